@@ -1,0 +1,157 @@
+/*
+ * rrmpg_b200.h -- C ABI of the B200 ensemble rainfall-runoff engine (librrmpg_b200.so).
+ *
+ * Drop-in boundary for the ONE data-parallel hot path of kratzert/RRMPG: the per-timestep
+ * storage-update recurrence of ABCModel, HBVEdu, GR4J, Cemaneige and CemaneigeGR4J evaluated
+ * for an ensemble of parameter sets.  In the reference this is a Python loop over members
+ * around one numba kernel call per member; each entry point below replaces one such loop +
+ * kernel pair with a single batched call (citations are file:line under the reference tree):
+ *
+ *   rrb_abc_simulate            run_abcmodel       rrmpg/models/abcmodel_model.py:16
+ *                               member loop        rrmpg/models/abcmodel.py:174-181
+ *   rrb_hbvedu_simulate         run_hbvedu         rrmpg/models/hbvedu_model.py:16
+ *                               member loop        rrmpg/models/hbvedu.py:199-209
+ *   rrb_gr4j_simulate           run_gr4j           rrmpg/models/gr4j_model.py:16
+ *                               member loop        rrmpg/models/gr4j.py:169-178
+ *   rrb_cemaneige_simulate      run_cemaneige      rrmpg/models/cemaneige_model.py:16
+ *                               member loop        rrmpg/models/cemaneige.py:227-240
+ *   rrb_cemaneigegr4j_simulate  run_cemaneigegr4j  rrmpg/models/cemaneigegr4j_model.py:17
+ *                               member loop        rrmpg/models/cemaneigegr4j.py:249-268
+ *   opts->qobs / opts->mse      per-member calc_mse loop of monte_carlo
+ *                                                  rrmpg/tools/monte_carlo.py:66-73
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch / numpy types.  All floating point data is IEEE
+ *     binary64, arrays are C-order and densely packed.
+ *   - `params` is the reference's structured record array viewed as a [N, k] double matrix
+ *     (field order = the model's `_dtype`, e.g. rrmpg/models/hbvedu.py:63-66).
+ *   - Outputs are laid out like the wrappers' arrays: [T, N] (rrmpg/models/hbvedu.py:191) and
+ *     [T, L, N] for the per-layer snow states (rrmpg/models/cemaneige.py:221-224).  Optional
+ *     ("storage") outputs may be NULL; pass all of a model's storages or none.  `qsim` itself
+ *     may be NULL when only the fused objective (opts->mse) is wanted.
+ *   - The caller owns every buffer.  The library never returns memory it allocated, never frees
+ *     caller memory and keeps no caller pointer after the call returns (RRB_MEM_HOST) or after
+ *     the work enqueued on opts->stream has completed (RRB_MEM_DEVICE).
+ *   - Input validation (negative precipitation, month range, ...) stays with the caller, as in
+ *     the reference where the Python wrappers raise before the kernel runs.  The kernels have
+ *     no numerical error path: NaN / Inf propagate exactly as in the numba code.
+ *   - Every function returns RRB_OK (0) or an RRB_E* code; rrb_last_error() gives the message
+ *     for the calling thread.  There is no CPU fallback: without a CUDA device the simulate
+ *     calls fail with RRB_ECUDA.
+ *   - Thread safety: calls are serialised per device by an internal mutex.
+ */
+#ifndef RRMPG_B200_H
+#define RRMPG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRB_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define RRB_API __attribute__((visibility("default")))
+#else
+#define RRB_API
+#endif
+
+enum rrb_status {
+    RRB_OK = 0,
+    RRB_EINVAL = 1,       /* bad argument (NULL pointer, T < 1, N < 0, L < 1, ...) */
+    RRB_ECUDA = 2,        /* CUDA runtime error (message in rrb_last_error) */
+    RRB_EUNSUPPORTED = 3, /* L > RRB_MAX_LAYERS, or a GR4J x4 > RRB_MAX_X4 */
+    RRB_ENOMEM = 4        /* device / pinned allocation failed */
+};
+
+enum rrb_mem {
+    RRB_MEM_HOST = 0,  /* every pointer argument is host memory (pinned memory is fastest) */
+    RRB_MEM_DEVICE = 1 /* every pointer argument is device memory on opts->device */
+};
+
+enum rrb_math {
+    RRB_MATH_FAST = 0,   /* table-driven pow/tanh, hoisted reciprocals; qsim within rtol 1e-10 of numba */
+    RRB_MATH_PRECISE = 1 /* the reference's operations one for one (CUDA libm pow/tanh, IEEE division) */
+};
+
+#define RRB_MAX_LAYERS 16 /* Cemaneige elevation layers per call */
+#define RRB_MAX_X4 64.0   /* GR4J unit hydrograph time base per member */
+
+typedef struct rrb_opts {
+    int32_t struct_size; /* = sizeof(rrb_opts); guards against ABI drift */
+    int32_t device;      /* CUDA device ordinal, -1 = the calling thread's current device */
+    int32_t mem;         /* enum rrb_mem */
+    int32_t math;        /* enum rrb_math */
+    void* stream;        /* RRB_MEM_DEVICE: cudaStream_t the work is enqueued on (NULL = default stream);
+                            the call returns without synchronising */
+    int32_t block;       /* threads per CTA, 0 = chosen from N and the SM count */
+    int32_t reserved;
+    double x4_max;       /* RRB_MEM_DEVICE, GR4J family: max x4 over params if the caller knows it;
+                            <= 0 lets the library reduce it on the device (one small sync) */
+    const double* qobs;  /* optional [T] observed discharge: fuses the objective into the kernel */
+    double* mse;         /* [N] out, required when qobs != NULL: mean((qobs - qsim[:, i])**2) */
+    int64_t slab_steps;  /* RRB_MEM_HOST: timesteps per pipelined time slab, 0 = automatic */
+} rrb_opts;
+
+/* ---- library / device management ------------------------------------------------------- */
+RRB_API int rrb_version(void);
+RRB_API int rrb_device_count(void);            /* number of visible CUDA devices, 0 when none / no driver */
+RRB_API int rrb_init(int device);              /* create the per-device context eagerly (optional) */
+RRB_API int rrb_shutdown(void);                /* release every context, stream and scratch pool */
+RRB_API const char* rrb_last_error(void);      /* message of the last failing call on this thread */
+RRB_API int rrb_synchronize(int device);       /* wait for all library work on the device */
+
+/* pinned host buffers for RRB_MEM_HOST callers (pooled; freeing returns the block to the pool) */
+RRB_API void* rrb_host_alloc(size_t bytes);
+RRB_API void rrb_host_free(void* ptr);
+RRB_API void rrb_host_pool_trim(void);         /* release pooled pinned blocks back to the OS */
+
+/* ---- ensemble simulations --------------------------------------------------------------- */
+
+/* ABC model.  params[N][3] = (a, b, c).  qsim, storage: [T, N].  qsim[0,:] = 0 (t = 0 is not
+ * simulated, abcmodel_model.py:53). */
+RRB_API int rrb_abc_simulate(const double* prec, int64_t T, double initial_state, const double* params, int64_t N,
+                     double* qsim, double* storage /* nullable */, const rrb_opts* opts);
+
+/* HBV-Edu.  month0[T] is the 0-based month index (the wrapper subtracts 1, hbvedu.py:164).
+ * PE_m, T_m: [12].  inits[4] = (snow, soil, s1, s2), always host memory.  params[N][11] =
+ * (T_t, DD, FC, Beta, C, PWP, K_0, K_1, K_2, K_p, L).  All outputs [T, N]; row 0 holds the
+ * initial states and qsim[0,:] = 0 (hbvedu_model.py:78-84). */
+RRB_API int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
+                        const double* T_m, int64_t T, const double* inits, const double* params, int64_t N,
+                        double* qsim, double* snow, double* soil, double* s1, double* s2 /* nullable x4 */,
+                        const rrb_opts* opts);
+
+/* GR4J.  s_init, r_init are fractions of x1 / x3 (gr4j_model.py:64-65).  params[N][4] =
+ * (x1, x2, x3, x4).  Every member is simulated (the reference returns after member 0 when
+ * return_storage=False, gr4j.py:178 -- a bug this API does not reproduce). */
+RRB_API int rrb_gr4j_simulate(const double* prec, const double* etp, int64_t T, double s_init, double r_init,
+                      const double* params, int64_t N, double* qsim, double* s_store, double* r_store /* nullable x2 */,
+                      const rrb_opts* opts);
+
+/* Cemaneige snow routine.  prec, mean_temp, frac_solid: the preprocessed [T, L] layer arrays
+ * (cemaneige.py:198-219).  params[N][param_stride], fields 0,1 = (CTG, Kf) -- param_stride = 2
+ * for Cemaneige records, 6 to read CemaneigeGR4J records in place.  outflow [T, N]; G, eTG
+ * [T, L, N]. */
+RRB_API int rrb_cemaneige_simulate(const double* prec, const double* mean_temp, const double* frac_solid, int64_t T,
+                           int64_t L, double snow_pack_init, double thermal_state_init, const double* params,
+                           int64_t param_stride, int64_t N, double* outflow, double* G, double* eTG /* nullable x2 */,
+                           const rrb_opts* opts);
+
+/* Cemaneige + GR4J, fused per timestep.  etp: [T].  inits[4] (always host memory) = (snow_pack_init,
+ * thermal_state_init, s_init, r_init).  params[N][6] = (CTG, Kf, x1, x2, x3, x4). */
+RRB_API int rrb_cemaneigegr4j_simulate(const double* prec, const double* mean_temp, const double* etp,
+                               const double* frac_solid, int64_t T, int64_t L, const double* inits,
+                               const double* params, int64_t N, double* qsim, double* G, double* eTG,
+                               double* s_store, double* r_store /* nullable x4 */, const rrb_opts* opts);
+
+/* ---- host-side checks of the FAST math (no GPU needed; used by the CPU test-suite) ------- */
+RRB_API void rrb_host_fast_pow(const double* x, const double* y, int64_t n, double* out);
+RRB_API void rrb_host_fast_exp2m1(const double* z, int64_t n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRMPG_B200_H */

@@ -1,0 +1,692 @@
+// rr_api.cu -- the C ABI of include/rrmpg_b200.h: per-device contexts, scratch pools, the
+// host-buffer path (H2D forcing + params, time-slab pipeline that overlaps the kernels with the
+// D2H of finished output rows) and the device-buffer path (everything enqueued on the caller's
+// stream).  No model arithmetic lives here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rrmpg_b200.h"
+#include "rr_kernels.h"
+#include "rr_math.cuh"
+
+namespace rrb {
+
+static_assert(RRB_MATH_FAST == RRB_MATH_FAST_ && RRB_MATH_PRECISE == RRB_MATH_PRECISE_, "math enum mismatch");
+static_assert(RRB_MAX_LAYERS == kCemaMaxLayers, "layer cap mismatch");
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define RRB_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? RRB_ENOMEM : RRB_ECUDA;                 \
+            return fail(code_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                           \
+    } while (0)
+
+// CTA size: the largest of {256,128,64,32} (<= max_block) whose grid leaves the SMs evenly
+// loaded.  With one thread per member a 65 536-member ensemble is only ~443 threads per SM, so
+// the rounding of CTAs per SM decides the makespan (e.g. 512 CTAs of 128 on 148 SMs = 3.46 -> 4
+// rounds of work on some SMs; 1024 CTAs of 64 = 6.92 -> 7, 1% imbalance).
+int pick_block(int64_t N, int sm_count, int max_block) {
+    if (sm_count <= 0) sm_count = 148;
+    int best = 32;
+    double best_eff = -1.0;
+    for (int b : {256, 128, 64, 32}) {
+        if (b > max_block) continue;
+        const int64_t ctas = (N + b - 1) / b;
+        const int64_t per_sm = (ctas + sm_count - 1) / sm_count;
+        const double eff = (double)N / ((double)per_sm * sm_count * b);
+        if (eff > best_eff * 1.04) {  // prefer the larger CTA unless a smaller one is >4% better
+            best_eff = eff;
+            best = b;
+        }
+    }
+    return best;
+}
+
+// max over members of one parameter field (device mode, when the caller gave no x4_max hint)
+__global__ void max_field_kernel(const double* __restrict__ params, int64_t N, int64_t stride, int field,
+                                 double* __restrict__ out) {
+    __shared__ double red[1024];
+    __shared__ int any_nan;
+    if (threadIdx.x == 0) any_nan = 0;
+    __syncthreads();
+    double m = -1.0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+        const double v = params[i * stride + field];
+        if (v != v) any_nan = 1;
+        if (v > m) m = v;
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s && red[threadIdx.x + s] > red[threadIdx.x]) red[threadIdx.x] = red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = any_nan ? NAN : red[0];
+}
+
+// ----------------------------------------------------------------------------------------
+// per-device context
+// ----------------------------------------------------------------------------------------
+enum BufSlot {
+    B_RAW0 = 0, B_RAW1, B_RAW2, B_RAW3, B_RAW4,  // uploaded raw forcing arrays
+    B_F,       // packed forcing
+    B_GT,      // Cemaneige G_tresh[L]
+    B_PARAMS,
+    B_STATE,
+    B_QOBS,
+    B_MSE,
+    B_SCALAR,
+    B_OUT0,    // output ring: B_OUT0 + 2*k + slot, k < 5
+    B_COUNT = B_OUT0 + 10
+};
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    std::mutex mu;
+    void* buf[B_COUNT] = {};
+    size_t cap[B_COUNT] = {};
+
+    int ensure(int slot, size_t bytes, void** out) {
+        if (bytes == 0) bytes = 16;
+        if (cap[slot] < bytes) {
+            if (buf[slot]) {
+                RRB_CUDA(cudaStreamSynchronize(compute));
+                RRB_CUDA(cudaStreamSynchronize(copy));
+                RRB_CUDA(cudaFree(buf[slot]));
+                buf[slot] = nullptr;
+                cap[slot] = 0;
+            }
+            size_t want = bytes + bytes / 8;  // a little slack so slowly growing sizes do not thrash
+            cudaError_t e = cudaMalloc(&buf[slot], want);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                want = bytes;
+                e = cudaMalloc(&buf[slot], want);
+            }
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                return fail(RRB_ENOMEM, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            }
+            cap[slot] = want;
+        }
+        *out = buf[slot];
+        return RRB_OK;
+    }
+    void release() {
+        for (int i = 0; i < B_COUNT; ++i) {
+            if (buf[i]) cudaFree(buf[i]);
+            buf[i] = nullptr;
+            cap[i] = 0;
+        }
+        for (int i = 0; i < 2; ++i) {
+            if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+            if (ev_free[i]) cudaEventDestroy(ev_free[i]);
+            ev_done[i] = ev_free[i] = nullptr;
+        }
+        if (compute) cudaStreamDestroy(compute);
+        if (copy) cudaStreamDestroy(copy);
+        compute = copy = nullptr;
+    }
+};
+
+static std::mutex g_ctx_mu;
+static std::map<int, std::unique_ptr<Ctx>> g_ctx;
+
+static int get_ctx(int device, Ctx** out) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(RRB_ECUDA, "no CUDA device available (%s); rrmpg_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0) RRB_CUDA(cudaGetDevice(&device));
+    if (device >= ndev) return fail(RRB_EINVAL, "device %d out of range (%d visible)", device, ndev);
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    auto it = g_ctx.find(device);
+    if (it == g_ctx.end()) {
+        RRB_CUDA(cudaSetDevice(device));
+        auto c = std::make_unique<Ctx>();
+        c->device = device;
+        RRB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+        RRB_CUDA(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+        RRB_CUDA(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            RRB_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+            RRB_CUDA(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        }
+        it = g_ctx.emplace(device, std::move(c)).first;
+    }
+    *out = it->second.get();
+    return RRB_OK;
+}
+
+struct Opts {
+    int device = -1, mem = RRB_MEM_HOST, math = RRB_MATH_FAST, block = 0;
+    cudaStream_t stream = nullptr;
+    double x4_max = 0.0;
+    const double* qobs = nullptr;
+    double* mse = nullptr;
+    int64_t slab_steps = 0;
+};
+
+static int parse_opts(const rrb_opts* o, Opts* out) {
+    if (!o) return RRB_OK;
+    if (o->struct_size != (int32_t)sizeof(rrb_opts))
+        return fail(RRB_EINVAL, "rrb_opts.struct_size = %d, expected %zu", o->struct_size, sizeof(rrb_opts));
+    if (o->mem != RRB_MEM_HOST && o->mem != RRB_MEM_DEVICE) return fail(RRB_EINVAL, "rrb_opts.mem = %d", o->mem);
+    if (o->math != RRB_MATH_FAST && o->math != RRB_MATH_PRECISE) return fail(RRB_EINVAL, "rrb_opts.math = %d", o->math);
+    if (o->block != 0 && (o->block < 32 || o->block > 1024 || (o->block % 32)))
+        return fail(RRB_EINVAL, "rrb_opts.block = %d (must be a multiple of 32 in [32, 1024])", o->block);
+    if (o->qobs && !o->mse) return fail(RRB_EINVAL, "rrb_opts.qobs given without rrb_opts.mse");
+    if (o->slab_steps < 0) return fail(RRB_EINVAL, "rrb_opts.slab_steps < 0");
+    out->device = o->device;
+    out->mem = o->mem;
+    out->math = o->math;
+    out->block = o->block;
+    out->stream = (cudaStream_t)o->stream;
+    out->x4_max = o->x4_max;
+    out->qobs = o->qobs;
+    out->mse = o->mse;
+    out->slab_steps = o->slab_steps;
+    return RRB_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// generic driver.  A Model supplies: how to upload + pack its forcing, its carry-state size,
+// its outputs, and how to launch one slab.
+// ----------------------------------------------------------------------------------------
+struct OutArr {
+    double* user;       // caller's buffer (host or device), nullable
+    int64_t row_elems;  // doubles per timestep (N or L*N)
+};
+
+struct Job {
+    int64_t T = 0, N = 0;
+    std::vector<OutArr> outs;
+    int state_slots = 0;
+    // launch(slab, out_ptrs (device, row0-relative), objective, cfg)
+    std::function<cudaError_t(const Slab&, double* const*, const Objective&, const LaunchCfg&)> launch;
+};
+
+static constexpr size_t kSlabTargetBytes = size_t(128) << 20;
+
+// Runs job.launch over [0, T).  Device mode: one launch straight into the caller's arrays.
+// Host mode: time slabs through a two-deep device ring; the D2H of slab k overlaps slab k+1.
+static int run_job(Ctx& c, const Opts& o, const Job& job, const double* d_qobs, double* d_mse) {
+    const int64_t T = job.T, N = job.N;
+    const int nout = (int)job.outs.size();
+    LaunchCfg cfg{};
+    cfg.block = o.block;
+    cfg.math = o.math;
+    cfg.sm_count = c.sm_count;
+    Objective obj{d_qobs, d_mse, T};
+
+    if (o.mem == RRB_MEM_DEVICE) {
+        cfg.stream = o.stream;
+        std::vector<double*> ptrs(nout);
+        for (int k = 0; k < nout; ++k) ptrs[k] = job.outs[k].user;
+        Slab slab{0, T, 0, nullptr, 0};
+        RRB_CUDA(job.launch(slab, ptrs.data(), obj, cfg));
+        return RRB_OK;
+    }
+
+    cfg.stream = c.compute;
+    int64_t bytes_per_step = 0;
+    for (auto& a : job.outs)
+        if (a.user) bytes_per_step += a.row_elems * (int64_t)sizeof(double);
+    int64_t steps = T;
+    if (bytes_per_step > 0) {
+        steps = o.slab_steps > 0 ? o.slab_steps : (int64_t)(kSlabTargetBytes / (size_t)bytes_per_step);
+        if (o.slab_steps == 0 && steps >= 64) steps &= ~int64_t(63);
+        steps = std::max<int64_t>(1, std::min(steps, T));
+        // two slabs of (almost) everything gain nothing over one
+        if (o.slab_steps == 0 && steps * 2 > T) steps = T;
+    }
+    const int nslabs = (int)((T + steps - 1) / steps);
+    const bool ring = nslabs > 1;
+
+    double* state = nullptr;
+    if (ring) {
+        void* p;
+        int rc = c.ensure(B_STATE, sizeof(double) * (size_t)job.state_slots * (size_t)N, &p);
+        if (rc) return rc;
+        state = (double*)p;
+    }
+    std::vector<double*> dev[2];
+    for (int s = 0; s < (ring ? 2 : 1); ++s) {
+        dev[s].assign(nout, nullptr);
+        for (int k = 0; k < nout; ++k) {
+            if (!job.outs[k].user) continue;
+            void* p;
+            int rc = c.ensure(B_OUT0 + 2 * k + s, sizeof(double) * (size_t)steps * (size_t)job.outs[k].row_elems, &p);
+            if (rc) return rc;
+            dev[s][k] = (double*)p;
+        }
+    }
+    for (int k = 0; k < nslabs; ++k) {
+        const int s = k & 1;
+        const int64_t t0 = (int64_t)k * steps, t1 = std::min(T, t0 + steps);
+        if (k >= 2) RRB_CUDA(cudaStreamWaitEvent(c.compute, c.ev_free[s], 0));
+        Slab slab{t0, t1, t0, state, ring ? 1 : 0};
+        RRB_CUDA(job.launch(slab, dev[s].data(), obj, cfg));
+        RRB_CUDA(cudaEventRecord(c.ev_done[s], c.compute));
+        RRB_CUDA(cudaStreamWaitEvent(c.copy, c.ev_done[s], 0));
+        for (int j = 0; j < nout; ++j) {
+            if (!job.outs[j].user) continue;
+            const size_t row = (size_t)job.outs[j].row_elems;
+            RRB_CUDA(cudaMemcpyAsync(job.outs[j].user + (size_t)t0 * row, dev[s][j],
+                                     sizeof(double) * (size_t)(t1 - t0) * row, cudaMemcpyDeviceToHost, c.copy));
+        }
+        RRB_CUDA(cudaEventRecord(c.ev_free[s], c.copy));
+    }
+    if (o.qobs) {
+        RRB_CUDA(cudaStreamWaitEvent(c.copy, c.ev_done[(nslabs - 1) & 1], 0));
+        RRB_CUDA(cudaMemcpyAsync(o.mse, d_mse, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, c.copy));
+    }
+    RRB_CUDA(cudaStreamSynchronize(c.copy));
+    RRB_CUDA(cudaStreamSynchronize(c.compute));
+    return RRB_OK;
+}
+
+// upload helper (host mode) / pass-through (device mode)
+template <class T_>
+static int stage_in(Ctx& c, const Opts& o, int slot, const T_* src, size_t count, const T_** out) {
+    if (o.mem == RRB_MEM_DEVICE || src == nullptr) {
+        *out = src;
+        return RRB_OK;
+    }
+    void* p;
+    int rc = c.ensure(slot, sizeof(T_) * count, &p);
+    if (rc) return rc;
+    RRB_CUDA(cudaMemcpyAsync(p, src, sizeof(T_) * count, cudaMemcpyHostToDevice, c.compute));
+    *out = (const T_*)p;
+    return RRB_OK;
+}
+
+struct Prepared {
+    Ctx* c = nullptr;
+    Opts o;
+    cudaStream_t s = nullptr;  // stream the prologue (uploads, packing) runs on
+    const double* d_params = nullptr;
+    const double* d_qobs = nullptr;
+    double* d_mse = nullptr;
+};
+
+static int prepare(const rrb_opts* opts, int64_t T, int64_t N, const double* params, int64_t pwidth, Prepared* P) {
+    int rc = parse_opts(opts, &P->o);
+    if (rc) return rc;
+    if (T < 1) return fail(RRB_EINVAL, "T = %lld (need at least one timestep)", (long long)T);
+    if (N < 0) return fail(RRB_EINVAL, "N = %lld", (long long)N);
+    if (N > 0 && !params) return fail(RRB_EINVAL, "params is NULL");
+    rc = get_ctx(P->o.device, &P->c);
+    if (rc) return rc;
+    RRB_CUDA(cudaSetDevice(P->c->device));
+    P->s = (P->o.mem == RRB_MEM_DEVICE) ? P->o.stream : P->c->compute;
+    return RRB_OK;
+}
+
+static int stage_common(Prepared* P, int64_t T, int64_t N, const double* params, int64_t pwidth) {
+    int rc = stage_in(*P->c, P->o, B_PARAMS, params, (size_t)(N * pwidth), &P->d_params);
+    if (rc) return rc;
+    if (P->o.qobs) {
+        rc = stage_in(*P->c, P->o, B_QOBS, P->o.qobs, (size_t)T, &P->d_qobs);
+        if (rc) return rc;
+        if (P->o.mem == RRB_MEM_DEVICE) {
+            P->d_mse = P->o.mse;
+        } else {
+            void* p;
+            rc = P->c->ensure(B_MSE, sizeof(double) * (size_t)std::max<int64_t>(N, 1), &p);
+            if (rc) return rc;
+            P->d_mse = (double*)p;
+        }
+    }
+    return RRB_OK;
+}
+
+static int resolve_x4_max(Prepared* P, const double* host_or_dev_params, int64_t N, int64_t stride, int field,
+                          double* out) {
+    if (P->o.mem == RRB_MEM_HOST) {
+        double m = -1.0;
+        bool nan = false;
+        for (int64_t i = 0; i < N; ++i) {
+            const double v = host_or_dev_params[i * stride + field];
+            if (v != v) nan = true;
+            if (v > m) m = v;
+        }
+        *out = nan ? NAN : m;
+        return RRB_OK;
+    }
+    if (P->o.x4_max > 0) {
+        *out = P->o.x4_max;
+        return RRB_OK;
+    }
+    void* d;
+    int rc = P->c->ensure(B_SCALAR, sizeof(double), &d);
+    if (rc) return rc;
+    max_field_kernel<<<1, 1024, 0, P->s>>>(P->d_params, N, stride, field, (double*)d);
+    RRB_CUDA(cudaGetLastError());
+    RRB_CUDA(cudaMemcpyAsync(out, d, sizeof(double), cudaMemcpyDeviceToHost, P->s));
+    RRB_CUDA(cudaStreamSynchronize(P->s));
+    return RRB_OK;
+}
+
+}  // namespace rrb
+
+using namespace rrb;
+
+// ----------------------------------------------------------------------------------------
+// C ABI
+// ----------------------------------------------------------------------------------------
+extern "C" {
+
+int rrb_version(void) { return RRB_VERSION; }
+
+int rrb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rrb_init(int device) {
+    Ctx* c;
+    return get_ctx(device, &c);
+}
+
+int rrb_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    for (auto& kv : g_ctx) {
+        cudaSetDevice(kv.first);
+        cudaDeviceSynchronize();
+        kv.second->release();
+    }
+    g_ctx.clear();
+    rrb_host_pool_trim();
+    return RRB_OK;
+}
+
+const char* rrb_last_error(void) { return g_err.c_str(); }
+
+int rrb_synchronize(int device) {
+    Ctx* c;
+    int rc = get_ctx(device, &c);
+    if (rc) return rc;
+    RRB_CUDA(cudaSetDevice(c->device));
+    RRB_CUDA(cudaDeviceSynchronize());
+    return RRB_OK;
+}
+
+// ---- pinned host pool ----
+static std::mutex g_pin_mu;
+static std::multimap<size_t, void*> g_pin_free;
+static std::map<void*, size_t> g_pin_live;
+
+void* rrb_host_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = g_pin_free.lower_bound(bytes);
+    if (it != g_pin_free.end() && it->first <= bytes + bytes / 4 + 4096) {
+        void* p = it->second;
+        g_pin_live[p] = it->first;
+        g_pin_free.erase(it);
+        return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        // make room and retry once
+        for (auto& kv : g_pin_free) cudaFreeHost(kv.second);
+        g_pin_free.clear();
+        e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            fail(RRB_ENOMEM, "cudaHostAlloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            return nullptr;
+        }
+    }
+    g_pin_live[p] = bytes;
+    return p;
+}
+
+void rrb_host_free(void* ptr) {
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = g_pin_live.find(ptr);
+    if (it == g_pin_live.end()) return;
+    g_pin_free.emplace(it->second, ptr);
+    g_pin_live.erase(it);
+}
+
+void rrb_host_pool_trim(void) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (auto& kv : g_pin_free) cudaFreeHost(kv.second);
+    g_pin_free.clear();
+}
+
+// ---- ABC ----
+int rrb_abc_simulate(const double* prec, int64_t T, double initial_state, const double* params, int64_t N,
+                     double* qsim, double* storage, const rrb_opts* opts) {
+    Prepared P;
+    int rc = prepare(opts, T, N, params, 3, &P);
+    if (rc) return rc;
+    if (!prec) return fail(RRB_EINVAL, "prec is NULL");
+    if (!qsim && !P.o.qobs) return fail(RRB_EINVAL, "nothing to compute: qsim is NULL and no objective requested");
+    if (N == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    const double* d_prec;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)T, &d_prec))) return rc;
+    if ((rc = stage_common(&P, T, N, params, 3))) return rc;
+    void* F;
+    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, kAbcTT) * kAbcR, &F))) return rc;
+    RRB_CUDA(pack_abc(d_prec, T, (double*)F, P.s));
+    Job job;
+    job.T = T; job.N = N;
+    job.outs = {{qsim, N}, {storage, N}};
+    job.state_slots = state_slots_abc();
+    const double* dp = P.d_params;
+    job.launch = [=](const Slab& sl, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
+        return launch_abc((const double*)F, T, initial_state, dp, N, out[0], out[1], sl, ob, cfg);
+    };
+    return run_job(*P.c, P.o, job, P.d_qobs, P.d_mse);
+}
+
+// ---- HBV-Edu ----
+int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
+                        const double* T_m, int64_t T, const double* inits, const double* params, int64_t N,
+                        double* qsim, double* snow, double* soil, double* s1, double* s2, const rrb_opts* opts) {
+    Prepared P;
+    int rc = prepare(opts, T, N, params, 11, &P);
+    if (rc) return rc;
+    if (!temp || !prec || !month0 || !PE_m || !T_m || !inits) return fail(RRB_EINVAL, "NULL forcing / inits pointer");
+    const int nst = (snow != nullptr) + (soil != nullptr) + (s1 != nullptr) + (s2 != nullptr);
+    if (nst != 0 && nst != 4) return fail(RRB_EINVAL, "pass all four storage outputs or none");
+    if (!qsim && !P.o.qobs && nst == 0) return fail(RRB_EINVAL, "nothing to compute");
+    if (N == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    const double *d_temp, *d_prec, *d_pe, *d_tm;
+    const int8_t* d_month;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, temp, (size_t)T, &d_temp))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW1, prec, (size_t)T, &d_prec))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW2, month0, (size_t)T, &d_month))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW3, PE_m, (size_t)12, &d_pe))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW4, T_m, (size_t)12, &d_tm))) return rc;
+    if ((rc = stage_common(&P, T, N, params, 11))) return rc;
+    double in4[4];
+    memcpy(in4, inits, sizeof(in4));  // inits is host memory in both modes
+    void* F;
+    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, kHbvTT) * kHbvR, &F))) return rc;
+    RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.s));
+    Job job;
+    job.T = T; job.N = N;
+    job.outs = {{qsim, N}, {snow, N}, {soil, N}, {s1, N}, {s2, N}};
+    job.state_slots = state_slots_hbvedu();
+    const double* dp = P.d_params;
+    const double i0 = in4[0], i1 = in4[1], i2 = in4[2], i3 = in4[3];
+    job.launch = [=](const Slab& sl, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
+        const double in[4] = {i0, i1, i2, i3};
+        return launch_hbvedu((const double*)F, T, in, dp, N, out[0], out[1], out[2], out[3], out[4], sl, ob, cfg);
+    };
+    return run_job(*P.c, P.o, job, P.d_qobs, P.d_mse);
+}
+
+// ---- GR4J ----
+int rrb_gr4j_simulate(const double* prec, const double* etp, int64_t T, double s_init, double r_init,
+                      const double* params, int64_t N, double* qsim, double* s_store, double* r_store,
+                      const rrb_opts* opts) {
+    Prepared P;
+    int rc = prepare(opts, T, N, params, 4, &P);
+    if (rc) return rc;
+    if (!prec || !etp) return fail(RRB_EINVAL, "NULL forcing pointer");
+    if ((s_store != nullptr) != (r_store != nullptr)) return fail(RRB_EINVAL, "pass both storage outputs or none");
+    if (!qsim && !P.o.qobs && !s_store) return fail(RRB_EINVAL, "nothing to compute");
+    if (N == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    const double *d_prec, *d_etp;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)T, &d_prec))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW1, etp, (size_t)T, &d_etp))) return rc;
+    if ((rc = stage_common(&P, T, N, params, 4))) return rc;
+    double x4_max;
+    if ((rc = resolve_x4_max(&P, params, N, 4, 3, &x4_max))) return rc;
+    if (!(x4_max <= RRB_MAX_X4))
+        return fail(RRB_EUNSUPPORTED, "GR4J x4 up to %g in this batch; the unit hydrograph buffers support x4 <= %g",
+                    x4_max, RRB_MAX_X4);
+    void* F;
+    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, kGr4jTT) * kGr4jR, &F))) return rc;
+    RRB_CUDA(pack_gr4j(d_prec, d_etp, T, (double*)F, P.s));
+    Job job;
+    job.T = T; job.N = N;
+    job.outs = {{qsim, N}, {s_store, N}, {r_store, N}};
+    job.state_slots = state_slots_gr4j(x4_max);
+    const double* dp = P.d_params;
+    job.launch = [=](const Slab& sl, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
+        return launch_gr4j((const double*)F, T, s_init, r_init, dp, N, x4_max, out[0], out[1], out[2], sl, ob, cfg);
+    };
+    return run_job(*P.c, P.o, job, P.d_qobs, P.d_mse);
+}
+
+// ---- Cemaneige ----
+int rrb_cemaneige_simulate(const double* prec, const double* mean_temp, const double* frac_solid, int64_t T,
+                           int64_t L, double snow_pack_init, double thermal_state_init, const double* params,
+                           int64_t param_stride, int64_t N, double* outflow, double* G, double* eTG,
+                           const rrb_opts* opts) {
+    Prepared P;
+    int rc = prepare(opts, T, N, params, param_stride, &P);
+    if (rc) return rc;
+    if (!prec || !mean_temp || !frac_solid) return fail(RRB_EINVAL, "NULL forcing pointer");
+    if (L < 1) return fail(RRB_EINVAL, "L = %lld", (long long)L);
+    if (L > RRB_MAX_LAYERS) return fail(RRB_EUNSUPPORTED, "L = %lld elevation layers (max %d)", (long long)L, RRB_MAX_LAYERS);
+    if (param_stride < 2) return fail(RRB_EINVAL, "param_stride = %lld (< 2)", (long long)param_stride);
+    if ((G != nullptr) != (eTG != nullptr)) return fail(RRB_EINVAL, "pass both storage outputs or none");
+    if (!outflow && !P.o.qobs && !G) return fail(RRB_EINVAL, "nothing to compute");
+    if (N == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    const double *d_prec, *d_mt, *d_fr;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(T * L), &d_prec))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(T * L), &d_mt))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW2, frac_solid, (size_t)(T * L), &d_fr))) return rc;
+    if ((rc = stage_common(&P, T, N, params, param_stride))) return rc;
+    const int LC = cema_layer_class((int)L);
+    void *F, *gt;
+    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, cema_TT(LC)) * cema_R(LC), &F))) return rc;
+    if ((rc = P.c->ensure(B_GT, sizeof(double) * kCemaMaxLayers, &gt))) return rc;
+    RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, nullptr, T, (int)L, (double*)F, (double*)gt, P.s));
+    Job job;
+    job.T = T; job.N = N;
+    job.outs = {{outflow, N}, {G, L * N}, {eTG, L * N}};
+    job.state_slots = state_slots_cemaneige((int)L);
+    const double* dp = P.d_params;
+    job.launch = [=](const Slab& sl, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
+        return launch_cemaneige((const double*)F, (const double*)gt, T, (int)L, snow_pack_init, thermal_state_init, dp,
+                                param_stride, N, out[0], out[1], out[2], sl, ob, cfg);
+    };
+    return run_job(*P.c, P.o, job, P.d_qobs, P.d_mse);
+}
+
+// ---- Cemaneige + GR4J ----
+int rrb_cemaneigegr4j_simulate(const double* prec, const double* mean_temp, const double* etp,
+                               const double* frac_solid, int64_t T, int64_t L, const double* inits,
+                               const double* params, int64_t N, double* qsim, double* G, double* eTG,
+                               double* s_store, double* r_store, const rrb_opts* opts) {
+    Prepared P;
+    int rc = prepare(opts, T, N, params, 6, &P);
+    if (rc) return rc;
+    if (!prec || !mean_temp || !etp || !frac_solid || !inits) return fail(RRB_EINVAL, "NULL forcing / inits pointer");
+    if (L < 1) return fail(RRB_EINVAL, "L = %lld", (long long)L);
+    if (L > RRB_MAX_LAYERS) return fail(RRB_EUNSUPPORTED, "L = %lld elevation layers (max %d)", (long long)L, RRB_MAX_LAYERS);
+    const int nst = (G != nullptr) + (eTG != nullptr) + (s_store != nullptr) + (r_store != nullptr);
+    if (nst != 0 && nst != 4) return fail(RRB_EINVAL, "pass all four storage outputs or none");
+    if (!qsim && !P.o.qobs && nst == 0) return fail(RRB_EINVAL, "nothing to compute");
+    if (N == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    const double *d_prec, *d_mt, *d_fr, *d_etp;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(T * L), &d_prec))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(T * L), &d_mt))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW2, frac_solid, (size_t)(T * L), &d_fr))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW3, etp, (size_t)T, &d_etp))) return rc;
+    if ((rc = stage_common(&P, T, N, params, 6))) return rc;
+    double in4[4];
+    memcpy(in4, inits, sizeof(in4));  // inits is host memory in both modes
+    double x4_max;
+    if ((rc = resolve_x4_max(&P, params, N, 6, 5, &x4_max))) return rc;
+    if (!(x4_max <= RRB_MAX_X4))
+        return fail(RRB_EUNSUPPORTED, "GR4J x4 up to %g in this batch; the unit hydrograph buffers support x4 <= %g",
+                    x4_max, RRB_MAX_X4);
+    const int LC = cema_layer_class((int)L);
+    void *F, *gt;
+    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, cema_TT(LC)) * cema_R(LC), &F))) return rc;
+    if ((rc = P.c->ensure(B_GT, sizeof(double) * kCemaMaxLayers, &gt))) return rc;
+    RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, d_etp, T, (int)L, (double*)F, (double*)gt, P.s));
+    Job job;
+    job.T = T; job.N = N;
+    job.outs = {{qsim, N}, {G, L * N}, {eTG, L * N}, {s_store, N}, {r_store, N}};
+    job.state_slots = state_slots_cemaneigegr4j((int)L, x4_max);
+    const double* dp = P.d_params;
+    const double i0 = in4[0], i1 = in4[1], i2 = in4[2], i3 = in4[3];
+    job.launch = [=](const Slab& sl, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
+        const double in[4] = {i0, i1, i2, i3};
+        return launch_cemaneigegr4j((const double*)F, (const double*)gt, T, (int)L, in, dp, N, x4_max, out[0], out[1],
+                                    out[2], out[3], out[4], sl, ob, cfg);
+    };
+    return run_job(*P.c, P.o, job, P.d_qobs, P.d_mse);
+}
+
+// ---- host evaluation of the FAST math (CPU test-suite) ----
+void rrb_host_fast_pow(const double* x, const double* y, int64_t n, double* out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = fast_pow(x[i], y[i], &h_fast_tables);
+}
+void rrb_host_fast_exp2m1(const double* z, int64_t n, double* out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = fast_exp2m1_nonneg(z[i], &h_fast_tables);
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// rr_common.cuh -- shared device machinery for the ensemble recurrence kernels (sm_100a).
+//
+// Execution model (all five models):
+//   * one thread owns one ensemble member for the whole series; its stores (snow pack, soil
+//     moisture, routing stores, unit-hydrograph buffers) live in registers,
+//   * the member-independent forcing of the catchment is packed time-major as F[t][R] doubles
+//     and streamed HBM -> shared memory in tiles of TT timesteps by 1-D TMA bulk copies
+//     (cp.async.bulk ... mbarrier::complete_tx::bytes) issued by one elected thread, multi-stage
+//     ring guarded by mbarriers; every thread then reads F[t][*] as a shared-memory broadcast,
+//   * per step every warp stores 32 consecutive doubles of the [T, N] output row (256 B,
+//     streaming st.global.cs so the multi-GB output does not evict forcing tiles from L2).
+//
+// The kernels replace the serial member loops of the reference wrappers
+// (rrmpg/models/hbvedu.py:199-209 and siblings); each model body cites the numba kernel it
+// restates.  The translation unit is compiled with -fmad=false: the reference (numba without
+// fastmath) never contracts a*b+c, so neither does the PRECISE path; FAST paths ask for FMAs
+// explicitly with fma().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rrb {
+
+constexpr int kStages = 3;        // forcing ring depth
+constexpr int kMaxStateSlots = 80; // upper bound of doubles a member carries across time slabs
+
+// ----------------------------------------------------------------------------------------
+// mbarrier / TMA-1D primitives (PTX; SASS: SYNCS.*, UBLKCP)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// order prior generic-proxy reads of a smem buffer before the async proxy overwrites it
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// streaming (evict-first) stores of the output rows
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+
+// numba's lowering of Python max(0, x) / min(a, b) on floats (oracle/rr_oracle.c header)
+__device__ __forceinline__ double nb_max0(double x) { return (x > 0.0) ? x : 0.0; }
+__device__ __forceinline__ double nb_min(double a, double b) { return (b < a) ? b : a; }
+
+// ----------------------------------------------------------------------------------------
+// Forcing tile pipeline.
+//   F      : packed forcing [Tpad][R] (Tpad = ntiles*TT, zero padded), 16-byte aligned
+//   smem   : kStages * TT * R doubles + kStages mbarriers (dynamic shared memory)
+//   step(t, f) is called for every t in [t_begin, t_end) with f -> the R forcing values of t.
+// Every thread of the CTA must call this (it contains CTA-wide barriers).
+// ----------------------------------------------------------------------------------------
+template <int R, int TT, class Step>
+__device__ __forceinline__ void stream_forcing(const double* __restrict__ F, int64_t t_begin, int64_t t_end,
+                                               Step&& step) {
+    extern __shared__ __align__(128) unsigned char rrb_smem[];
+    double* tiles = reinterpret_cast<double*>(rrb_smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(rrb_smem + sizeof(double) * kStages * TT * R);
+    constexpr uint32_t kTileBytes = TT * R * sizeof(double);
+    static_assert(kTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+    if (t_end <= t_begin) return;
+    const int64_t k_begin = t_begin / TT;
+    const int64_t k_end = (t_end + TT - 1) / TT;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            const int64_t k = k_begin + s;
+            if (k < k_end) {
+                mbar_arrive_expect_tx(&full[s], kTileBytes);
+                tma_load_1d(tiles + (size_t)s * TT * R, F + (size_t)k * TT * R, kTileBytes, &full[s]);
+            }
+        }
+    }
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int64_t k = k_begin; k < k_end; ++k) {
+        mbar_wait(&full[stage], parity);
+        const double* tile = tiles + (size_t)stage * TT * R;
+        const int64_t t0 = k * TT;
+        const int lo = (int)((t_begin > t0) ? (t_begin - t0) : 0);
+        const int hi = (int)((t_end < t0 + TT) ? (t_end - t0) : TT);
+        if (lo == 0 && hi == TT) {
+#pragma unroll 4
+            for (int tt = 0; tt < TT; ++tt) step(t0 + tt, tile + tt * R);
+        } else {
+            for (int tt = lo; tt < hi; ++tt) step(t0 + tt, tile + tt * R);
+        }
+        __syncthreads();  // every thread is done reading this stage
+        if (threadIdx.x == 0 && k + kStages < k_end) {
+            fence_proxy_async_smem();
+            mbar_arrive_expect_tx(&full[stage], kTileBytes);
+            tma_load_1d(tiles + (size_t)stage * TT * R, F + (size_t)(k + kStages) * TT * R, kTileBytes,
+                        &full[stage]);
+        }
+        if (++stage == kStages) {
+            stage = 0;
+            parity ^= 1u;
+        }
+    }
+}
+
+// dynamic shared memory = [forcing ring | mbarriers | (FAST math tables)], rounded to 16 B
+template <int R, int TT>
+__host__ __device__ constexpr size_t forcing_smem_bytes() {
+    return (sizeof(double) * kStages * TT * R + sizeof(uint64_t) * kStages + 15) & ~size_t(15);
+}
+
+}  // namespace rrb

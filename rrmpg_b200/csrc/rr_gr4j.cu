@@ -1,0 +1,134 @@
+// rr_gr4j.cu -- GR4J ensemble kernel.
+// Restates run_gr4j (rrmpg/models/gr4j_model.py:16-157) for N members at once and replaces the
+// member loop of GR4J.simulate (rrmpg/models/gr4j.py:169-178).  Unlike that loop -- which
+// returns after member 0 when return_storage=False (gr4j.py:178) -- every member is simulated,
+// as the docstring (gr4j.py:94-97) promises.
+// Packed forcing per timestep: F[t] = { prec, etp }.  All T steps are simulated (t = 0 too).
+#include "rr_common.cuh"
+#include "rr_gr4j.cuh"
+#include "rr_kernels.h"
+
+namespace rrb {
+
+__global__ void gr4j_pack_kernel(const double* __restrict__ prec, const double* __restrict__ etp, int64_t T,
+                                 int64_t Tpad, double* __restrict__ F) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= Tpad) return;
+    double2 v = make_double2(0.0, 0.0);
+    if (t < T) {
+        v.x = prec[t];
+        v.y = etp[t];
+    }
+    reinterpret_cast<double2*>(F)[t] = v;
+}
+
+cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* F, cudaStream_t s) {
+    int64_t Tpad = padded_steps(T, kGr4jTT);
+    gr4j_pack_kernel<<<(unsigned)((Tpad + 255) / 256), 256, 0, s>>>(prec, etp, T, Tpad, F);
+    return cudaGetLastError();
+}
+
+template <class Member, bool FAST>
+__global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double r_init,
+                            const double* __restrict__ params, int64_t N, double* __restrict__ qsim,
+                            double* __restrict__ s_store, double* __restrict__ r_store, Slab slab,
+                            Objective obj) {
+    const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool active = gi < N;
+    const int64_t i = active ? gi : N - 1;
+    const bool STORAGE = s_store != nullptr, OBJ = obj.qobs != nullptr;  // CTA-uniform
+    Member m;
+    m.init(params + 4 * i, s_init, r_init);  // record = (x1, x2, x3, x4), rrmpg/models/gr4j.py:57-60
+    double acc = 0.0;
+    if (slab.t_begin > 0) {
+        m.load(slab.state, N, i);
+        if (OBJ) acc = slab.state[(int64_t)Member::kStateSlots * N + i];
+    }
+    const int64_t off = i - slab.row0 * N;
+    double* q_o = qsim ? qsim + off : nullptr;
+
+    extern __shared__ __align__(128) unsigned char rrb_smem[];
+    const FastTables* tb = nullptr;
+    if (FAST) tb = fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<kGr4jR, kGr4jTT>());
+
+    stream_forcing<kGr4jR, kGr4jTT>(F, slab.t_begin, slab.t_end, [&](int64_t t, const double* f) {
+        const double2 pe = *reinterpret_cast<const double2*>(f);
+        const double qv = m.step(pe.x, pe.y, tb);
+        if (active) {
+            if (q_o) st_stream(q_o + t * N, qv);
+            if (STORAGE) {
+                st_stream(s_store + off + t * N, m.S);
+                st_stream(r_store + off + t * N, m.R);
+            }
+        }
+        if (OBJ) {
+            const double d = obj.qobs[t] - qv;
+            acc += d * d;
+        }
+    });
+
+    if (active) {
+        if (slab.save_state) {
+            m.save(slab.state, N, i);
+            if (OBJ) slab.state[(int64_t)Member::kStateSlots * N + i] = acc;
+        }
+        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i] = acc / (double)obj.T;
+    }
+}
+
+// unit-hydrograph capacity classes: (C1, C2) covers x4 <= C1 (C2 = 2 C1 + 1)
+static int uh_class(double x4_max) {
+    if (!(x4_max <= 64.0)) return -1;
+    if (x4_max <= 3.0) return 0;   // default bounds (1.1, 2.9), rrmpg/models/gr4j.py:54
+    if (x4_max <= 4.0) return 1;   // the reference's CemaneigeGR4J fixture (x4 = 3.098)
+    if (x4_max <= 10.0) return 2;  // Hyst-family bounds go to 10
+    return 3;                      // local-memory fallback
+}
+
+int state_slots_gr4j(double x4_max) {
+    switch (uh_class(x4_max)) {
+        case 0: return 2 + 3 + 7 + 1;
+        case 1: return 2 + 4 + 9 + 1;
+        case 2: return 2 + 10 + 21 + 1;
+        default: return Gr4jMemberDyn::kStateSlots + 1;
+    }
+}
+
+template <class Member, bool FAST>
+static cudaError_t launch_variant(const double* F, double s_init, double r_init, const double* params, int64_t N,
+                                  double* qsim, double* s_store, double* r_store, const Slab& slab,
+                                  const Objective& obj, const LaunchCfg& cfg) {
+    const int block = cfg.block > 0 ? cfg.block : pick_block(N, cfg.sm_count, 128);
+    const unsigned grid = (unsigned)((N + block - 1) / block);
+    const size_t smem = forcing_smem_bytes<kGr4jR, kGr4jTT>() + (FAST ? fastmath_smem_bytes() : 0);
+    gr4j_kernel<Member, FAST><<<grid, block, smem, cfg.stream>>>(F, s_init, r_init, params, N, qsim, s_store, r_store,
+                                                                 slab, obj);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gr4j(const double* F, int64_t T, double s_init, double r_init, const double* params,
+                        int64_t N, double x4_max, double* qsim, double* s_store, double* r_store,
+                        const Slab& slab, const Objective& obj, const LaunchCfg& cfg) {
+    (void)T;
+    if (N <= 0) return cudaSuccess;
+    const bool fast = cfg.math == RRB_MATH_FAST_;
+#define RRB_GO(M_, F_) return launch_variant<M_, F_>(F, s_init, r_init, params, N, qsim, s_store, r_store, slab, obj, cfg)
+    switch (uh_class(x4_max)) {
+        case 0:
+            if (fast) RRB_GO(Gr4jUh3F, true);
+            RRB_GO(Gr4jUh3P, false);
+        case 1:
+            if (fast) RRB_GO(Gr4jUh4F, true);
+            RRB_GO(Gr4jUh4P, false);
+        case 2:
+            if (fast) RRB_GO(Gr4jUh10F, true);
+            RRB_GO(Gr4jUh10P, false);
+        case 3:
+            RRB_GO(Gr4jMemberDyn, false);
+        default:
+            return cudaErrorInvalidValue;
+    }
+#undef RRB_GO
+}
+
+}  // namespace rrb

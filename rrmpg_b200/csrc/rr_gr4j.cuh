@@ -1,0 +1,235 @@
+// rr_gr4j.cuh -- per-member GR4J state machine shared by the GR4J and CemaneigeGR4J kernels.
+// Restates run_gr4j (rrmpg/models/gr4j_model.py:16-157) and its S-curves (:159-192).
+//
+// The reference sizes the two unit-hydrograph buffers per member (num_uh1 = ceil(x4),
+// num_uh2 = ceil(2 x4 + 1), :68-69).  Here they are compile-time-sized register arrays
+// (C1, C2 >= the largest length in the batch, chosen by the host from max x4): ordinates
+// beyond a member's own length are exactly 0 (S-curve differences 1 - 1) and the member's last
+// real slot is written without reading its padded neighbour, so the padded arithmetic is
+// value-identical to the reference's variable-length loops (:130-136).
+#pragma once
+#include "rr_common.cuh"
+#include "rr_math.cuh"
+
+namespace rrb {
+
+__device__ __forceinline__ double gr4j_s_curve1(int t, double x4) {  // gr4j_model.py:159-173
+    if (t <= 0) return 0.0;
+    else if ((double)t < x4) return pow((double)t / x4, 2.5);
+    else return 1.0;
+}
+__device__ __forceinline__ double gr4j_s_curve2(int t, double x4) {  // gr4j_model.py:176-192
+    if (t <= 0) return 0.0;
+    else if ((double)t <= x4) return 0.5 * pow((double)t / x4, 2.5);
+    else if ((double)t < 2 * x4) return 1 - 0.5 * pow(2 - (double)t / x4, 2.5);
+    else return 1.0;
+}
+
+template <int C1, int C2, int MATH>
+struct Gr4jMember {
+    double x1, x2, x3;
+    double inv_x1, inv_x3, k_tanh;  // FAST: 1/x1, 1/x3, 2 log2(e) / x1
+    int n1, n2;
+    double o1[C1], o2[C2];  // unit hydrograph ordinates
+    double u1[C1], u2[C2];  // routed water still in the unit hydrographs
+    double S, R;            // production / routing store
+
+    static constexpr int kStateSlots = 2 + C1 + C2;
+
+    __device__ __forceinline__ void init(const double* p /* x1,x2,x3,x4 */, double s_init, double r_init) {
+        x1 = p[0]; x2 = p[1]; x3 = p[2];
+        const double x4 = p[3];
+        inv_x1 = 1.0 / x1; inv_x3 = 1.0 / x3;
+        k_tanh = 2.8853900817779268 / x1;  // 2 / ln 2
+        S = s_init * x1;  // :64
+        R = r_init * x3;  // :65
+        n1 = (int)ceil(x4);          // :68
+        n2 = (int)ceil(2 * x4 + 1);  // :69
+        n1 = n1 < 1 ? 1 : (n1 > C1 ? C1 : n1);
+        n2 = n2 < 1 ? 1 : (n2 > C2 ? C2 : n2);
+#pragma unroll
+        for (int j = 1; j <= C1; ++j) {
+            o1[j - 1] = gr4j_s_curve1(j, x4) - gr4j_s_curve1(j - 1, x4);  // :75-76
+            u1[j - 1] = 0.0;
+        }
+#pragma unroll
+        for (int j = 1; j <= C2; ++j) {
+            o2[j - 1] = gr4j_s_curve2(j, x4) - gr4j_s_curve2(j - 1, x4);  // :78-79
+            u2[j - 1] = 0.0;
+        }
+    }
+
+    __device__ __forceinline__ void load(const double* state, int64_t N, int64_t i) {
+        S = state[0 * N + i];
+        R = state[1 * N + i];
+#pragma unroll
+        for (int j = 0; j < C1; ++j) u1[j] = state[(2 + j) * N + i];
+#pragma unroll
+        for (int j = 0; j < C2; ++j) u2[j] = state[(2 + C1 + j) * N + i];
+    }
+    __device__ __forceinline__ void save(double* state, int64_t N, int64_t i) const {
+        state[0 * N + i] = S;
+        state[1 * N + i] = R;
+#pragma unroll
+        for (int j = 0; j < C1; ++j) state[(2 + j) * N + i] = u1[j];
+#pragma unroll
+        for (int j = 0; j < C2; ++j) state[(2 + C1 + j) * N + i] = u2[j];
+    }
+
+    // one timestep: P = precipitation (or Cemaneige liquid outflow), E = potential evapotranspiration
+    __device__ __forceinline__ double step(double P, double E, const FastTables* tb) {
+        const bool wet = P >= E;                   // :89
+        const double arg = wet ? P - E : E - P;    // p_n (:90) or pe_n (:101)
+        const double p_n = wet ? arg : 0.0;
+        double frac, perc, gw, q_r;
+        if (MATH == RRB_MATH_FAST_) {
+            const double sr = S * inv_x1;
+            // tanh(a) = m / (m + 2), m = expm1(2a): both branch formulas collapse to num*m / (2 + c*m)
+            const double m = fast_exp2m1_nonneg(arg * k_tanh, tb);
+            const double num = wet ? x1 * (1 - sr * sr) : S * (2 - sr);
+            const double c = wet ? 1 + sr : 2 - sr;
+            frac = (num * m) / fma(c, m, 2.0);
+        } else {
+            const double sr = S / x1;
+            const double th = tanh(arg / x1);
+            const double num = wet ? (x1 * (1 - sr * sr)) * th : (S * (2 - sr)) * th;  // :95 / :107
+            const double den = wet ? 1 + sr * th : 1 + (1 - sr) * th;                  // :96 / :108
+            frac = num / den;
+        }
+        const double p_s = wet ? frac : 0.0;
+        const double e_s = wet ? 0.0 : frac;
+        S = S - e_s + p_s;  // :114
+        if (MATH == RRB_MATH_FAST_) {
+            const double u = (4.0 / 9.0 * S) * inv_x1;
+            const double u2 = u * u;
+            perc = S * (1 - fast_rsqrt4_ge1(1 + u2 * u2));
+        } else {
+            const double u = 4.0 / 9.0 * S / x1;
+            const double u2 = u * u;
+            perc = S * (1 - pow(1 + u2 * u2, -0.25));  // :117
+        }
+        S = S - perc;                           // :120
+        const double p_r = perc + (p_n - p_s);  // :123
+        const double p1 = 0.9 * p_r;            // :126
+        const double p2 = 0.1 * p_r;            // :127
+        // unit hydrographs, :130-136
+#pragma unroll
+        for (int j = 0; j < C1 - 1; ++j) {
+            const double add = o1[j] * p1;
+            u1[j] = (j == n1 - 1) ? add : u1[j + 1] + add;
+        }
+        u1[C1 - 1] = o1[C1 - 1] * p1;
+#pragma unroll
+        for (int j = 0; j < C2 - 1; ++j) {
+            const double add = o2[j] * p2;
+            u2[j] = (j == n2 - 1) ? add : u2[j + 1] + add;
+        }
+        u2[C2 - 1] = o2[C2 - 1] * p2;
+        if (MATH == RRB_MATH_FAST_) {
+            const double w = R * inv_x3;
+            gw = x2 * ((w * w) * (w * sqrt(w)));  // w^3.5 (NaN for w < 0, like pow)
+        } else {
+            gw = x2 * pow(R / x3, 3.5);  // :139
+        }
+        R = nb_max0(R + u1[0] + gw);  // :142
+        if (MATH == RRB_MATH_FAST_) {
+            const double v = R * inv_x3;
+            const double v2 = v * v;
+            q_r = R * (1 - fast_rsqrt4_ge1(1 + v2 * v2));
+        } else {
+            const double v = R / x3;
+            const double v2 = v * v;
+            q_r = R * (1 - pow(1 + v2 * v2, -0.25));  // :145
+        }
+        R = R - q_r;                            // :148
+        const double q_d = nb_max0(u2[0] + gw);  // :151
+        return q_r + q_d;                        // :154
+    }
+};
+
+// unit-hydrograph capacity classes used by the kernels
+using Gr4jUh3F = Gr4jMember<3, 7, RRB_MATH_FAST_>;
+using Gr4jUh3P = Gr4jMember<3, 7, RRB_MATH_PRECISE_>;
+using Gr4jUh4F = Gr4jMember<4, 9, RRB_MATH_FAST_>;
+using Gr4jUh4P = Gr4jMember<4, 9, RRB_MATH_PRECISE_>;
+using Gr4jUh10F = Gr4jMember<10, 21, RRB_MATH_FAST_>;
+using Gr4jUh10P = Gr4jMember<10, 21, RRB_MATH_PRECISE_>;
+
+// generic fallback for very long unit hydrographs (x4 beyond the register variants): buffers
+// in per-thread local memory with run-time lengths, PRECISE arithmetic only.  x4 <= 64.
+constexpr int kGr4jGenericC1 = 64, kGr4jGenericC2 = 129;
+
+struct Gr4jMemberDyn {
+    double x1, x2, x3;
+    int n1, n2;
+    double o1[kGr4jGenericC1], o2[kGr4jGenericC2];
+    double u1[kGr4jGenericC1], u2[kGr4jGenericC2];
+    double S, R;
+
+    static constexpr int kStateSlots = 2 + kGr4jGenericC1 + kGr4jGenericC2;
+
+    __device__ void init(const double* p, double s_init, double r_init) {
+        x1 = p[0]; x2 = p[1]; x3 = p[2];
+        const double x4 = p[3];
+        S = s_init * x1;
+        R = r_init * x3;
+        n1 = (int)ceil(x4);
+        n2 = (int)ceil(2 * x4 + 1);
+        n1 = n1 < 1 ? 1 : (n1 > kGr4jGenericC1 ? kGr4jGenericC1 : n1);
+        n2 = n2 < 1 ? 1 : (n2 > kGr4jGenericC2 ? kGr4jGenericC2 : n2);
+        for (int j = 1; j <= kGr4jGenericC1; ++j) {
+            o1[j - 1] = (j <= n1) ? gr4j_s_curve1(j, x4) - gr4j_s_curve1(j - 1, x4) : 0.0;
+            u1[j - 1] = 0.0;
+        }
+        for (int j = 1; j <= kGr4jGenericC2; ++j) {
+            o2[j - 1] = (j <= n2) ? gr4j_s_curve2(j, x4) - gr4j_s_curve2(j - 1, x4) : 0.0;
+            u2[j - 1] = 0.0;
+        }
+    }
+    __device__ void load(const double* state, int64_t N, int64_t i) {
+        S = state[0 * N + i];
+        R = state[1 * N + i];
+        for (int j = 0; j < kGr4jGenericC1; ++j) u1[j] = state[(2 + j) * N + i];
+        for (int j = 0; j < kGr4jGenericC2; ++j) u2[j] = state[(2 + kGr4jGenericC1 + j) * N + i];
+    }
+    __device__ void save(double* state, int64_t N, int64_t i) const {
+        state[0 * N + i] = S;
+        state[1 * N + i] = R;
+        for (int j = 0; j < kGr4jGenericC1; ++j) state[(2 + j) * N + i] = u1[j];
+        for (int j = 0; j < kGr4jGenericC2; ++j) state[(2 + kGr4jGenericC1 + j) * N + i] = u2[j];
+    }
+    __device__ double step(double P, double E, const FastTables*) {
+        const bool wet = P >= E;
+        const double arg = wet ? P - E : E - P;
+        const double p_n = wet ? arg : 0.0;
+        const double sr = S / x1;
+        const double th = tanh(arg / x1);
+        const double num = wet ? (x1 * (1 - sr * sr)) * th : (S * (2 - sr)) * th;
+        const double den = wet ? 1 + sr * th : 1 + (1 - sr) * th;
+        const double frac = num / den;
+        const double p_s = wet ? frac : 0.0;
+        const double e_s = wet ? 0.0 : frac;
+        S = S - e_s + p_s;
+        const double u = 4.0 / 9.0 * S / x1;
+        const double uu = u * u;
+        const double perc = S * (1 - pow(1 + uu * uu, -0.25));
+        S = S - perc;
+        const double p_r = perc + (p_n - p_s);
+        const double p1 = 0.9 * p_r;
+        const double p2 = 0.1 * p_r;
+        for (int j = 0; j < n1 - 1; ++j) u1[j] = u1[j + 1] + o1[j] * p1;
+        u1[n1 - 1] = o1[n1 - 1] * p1;
+        for (int j = 0; j < n2 - 1; ++j) u2[j] = u2[j + 1] + o2[j] * p2;
+        u2[n2 - 1] = o2[n2 - 1] * p2;
+        const double gw = x2 * pow(R / x3, 3.5);
+        R = nb_max0(R + u1[0] + gw);
+        const double v = R / x3;
+        const double vv = v * v;
+        const double q_r = R * (1 - pow(1 + vv * vv, -0.25));
+        R = R - q_r;
+        const double q_d = nb_max0(u2[0] + gw);
+        return q_r + q_d;
+    }
+};
+
+}  // namespace rrb

@@ -1,0 +1,91 @@
+// rr_kernels.h -- host-side launch interface between the C-ABI layer (rr_api.cu) and the
+// per-model kernel translation units.  Internal; the public boundary is include/rrmpg_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rrb {
+
+// One kernel launch simulates timesteps [t_begin, t_end) of every member.  Output buffers
+// are C-order [rows, N] (or [rows, L, N]) where row r holds timestep row0 + r, so a launch can
+// fill a whole [T, N] array (row0 = 0) or one time slab of a ring (row0 = t_begin).
+// state is a [slots, N] carry buffer: read when t_begin > 0, written when save_state != 0.
+struct Slab {
+    int64_t t_begin;
+    int64_t t_end;
+    int64_t row0;
+    double* state;
+    int save_state;
+};
+
+struct LaunchCfg {
+    cudaStream_t stream;
+    int block;  // threads per CTA (0 = auto from N and the SM count)
+    int math;   // RRB_MATH_FAST / RRB_MATH_PRECISE
+    int sm_count;
+};
+
+// fused per-member objective: when qobs != nullptr the kernels accumulate
+// sum_t (qobs[t] - q[t])^2 in a register (rrmpg/tools/monte_carlo.py:70-71 +
+// rrmpg/utils/metrics.py:131; carried across slabs through `state`) and the last slab writes
+// mse[i] = sum / T.
+struct Objective {
+    const double* qobs;  // [T] device, nullable
+    double* mse;         // [N] device: written by the launch whose slab ends at T
+    int64_t T;           // total series length (the divisor of np.mean)
+};
+
+int pick_block(int64_t N, int sm_count, int max_block);
+
+// ---- forcing tile geometry (doubles per timestep R, timesteps per tile TT) ----
+constexpr int kAbcR = 1, kAbcTT = 512;
+constexpr int kHbvR = 4, kHbvTT = 128;
+constexpr int kGr4jR = 2, kGr4jTT = 256;
+constexpr int kCemaTileDoubles = 1024;  // TT = kCemaTileDoubles / R
+constexpr int kCemaMaxLayers = 16;
+// layer capacity class LC of a run with L elevation layers; R and TT follow from LC
+inline int cema_layer_class(int L) { return L <= 1 ? 1 : (L <= 5 ? 5 : 16); }
+inline int cema_R(int LC) { return (3 * LC + 1 + 1) & ~1; }
+inline int cema_TT(int LC) { return kCemaTileDoubles / cema_R(LC); }
+
+inline int64_t padded_steps(int64_t T, int TT) { return ((T + TT - 1) / TT) * TT; }
+
+// ---- forcing packers (device pointers in, packed F[Tpad][R] out) ----
+cudaError_t pack_abc(const double* prec, int64_t T, double* F, cudaStream_t s);
+cudaError_t pack_hbvedu(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
+                        const double* T_m, int64_t T, double* F, cudaStream_t s);
+cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* F, cudaStream_t s);
+// writes F and g_tresh[L] (sequential np.mean semantics, rrmpg/models/cemaneige_model.py:80)
+cudaError_t pack_cemaneige(const double* prec, const double* mean_temp, const double* frac, const double* etp,
+                           int64_t T, int L, double* F, double* g_tresh, cudaStream_t s);
+
+// ---- model launches ----
+cudaError_t launch_abc(const double* F, int64_t T, double s0, const double* params, int64_t N, double* qsim,
+                       double* storage, const Slab& slab, const Objective& obj, const LaunchCfg& cfg);
+
+cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, const double* params, int64_t N,
+                          double* qsim, double* snow, double* soil, double* s1, double* s2, const Slab& slab,
+                          const Objective& obj, const LaunchCfg& cfg);
+
+// uh_cap: 0 = derive from x4_max
+cudaError_t launch_gr4j(const double* F, int64_t T, double s_init, double r_init, const double* params,
+                        int64_t N, double x4_max, double* qsim, double* s_store, double* r_store,
+                        const Slab& slab, const Objective& obj, const LaunchCfg& cfg);
+
+cudaError_t launch_cemaneige(const double* F, const double* g_tresh, int64_t T, int L, double g0, double e0,
+                             const double* params, int64_t pstride, int64_t N, double* outflow, double* G,
+                             double* eTG, const Slab& slab, const Objective& obj, const LaunchCfg& cfg);
+
+cudaError_t launch_cemaneigegr4j(const double* F, const double* g_tresh, int64_t T, int L, const double* inits4,
+                                 const double* params, int64_t N, double x4_max, double* qsim, double* G,
+                                 double* eTG, double* s_store, double* r_store, const Slab& slab,
+                                 const Objective& obj, const LaunchCfg& cfg);
+
+// number of carry slots a model needs in Slab::state
+int state_slots_abc();
+int state_slots_hbvedu();
+int state_slots_gr4j(double x4_max);
+int state_slots_cemaneige(int L);
+int state_slots_cemaneigegr4j(int L, double x4_max);
+
+}  // namespace rrb

@@ -1,0 +1,158 @@
+// rr_math.cuh -- FAST-path fp64 transcendentals for the recurrence kernels.
+//
+// The reference calls glibc pow/tanh once or more per member-timestep
+// (rrmpg/models/hbvedu_model.py:99, rrmpg/models/gr4j_model.py:95-96,117,139,145).  CUDA's libm
+// pow costs ~95 fp64 instructions, which makes the kernels fp64-issue-bound far below the HBM
+// roofline.  These replacements trade the last ulp for a 4x shorter instruction sequence:
+// table-driven log2 / exp2 (128-entry tables staged in shared memory, tables from
+// gen_math_tables.py), ~1e-15 relative accuracy, with the exotic operand ranges (zero,
+// negative, denormal, inf/nan, overflow) routed to the libm slow path so special-value
+// behaviour is unchanged.  The functions are __host__ __device__ so the algorithm and tables
+// are also checked on the CPU against glibc (rrb_host_fast_pow in rr_api.cu, tests/test_fastmath.py).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "rr_math_tables.h"
+
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#endif
+
+namespace rrb {
+
+enum { RRB_MATH_FAST_ = 0, RRB_MATH_PRECISE_ = 1 };
+
+struct FastTables {
+    double log2tab[2 * tables::kLogN];           // {invc, log2c}
+    unsigned long long exp2tab[tables::kExpN];   // bits(2^(j/128)) - (j << 45)
+    double exp2m1tab[tables::kExpN];             // 2^(j/128) - 1
+};
+
+#ifdef __CUDACC__
+static __device__ const FastTables d_fast_tables = {RRB_LOG2_TABLE, RRB_EXP2_TABLE, RRB_EXP2M1_TABLE};
+#endif
+static const FastTables h_fast_tables = {RRB_LOG2_TABLE, RRB_EXP2_TABLE, RRB_EXP2M1_TABLE};
+
+__host__ __device__ __forceinline__ uint64_t f64_bits(double x) {
+#ifdef __CUDA_ARCH__
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return u;
+#endif
+}
+__host__ __device__ __forceinline__ double bits_f64(uint64_t u) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)u);
+#else
+    double x;
+    memcpy(&x, &u, 8);
+    return x;
+#endif
+}
+
+// log2(x) for positive normal finite x.  |error| ~ 1e-16 * max(1, |log2 x|).
+__host__ __device__ __forceinline__ double fast_log2_normal(double x, const FastTables* tb) {
+    constexpr double A[7] = RRB_LOG2_POLY;
+    const uint64_t ix = f64_bits(x);
+    const uint64_t tmp = ix - tables::kLogOff;
+    const int i = (int)((tmp >> 45) & (tables::kLogN - 1));
+    const int k = (int)((int64_t)tmp >> 52);
+    const double z = bits_f64(ix - (tmp & 0xFFF0000000000000ULL));
+    const double invc = tb->log2tab[2 * i], log2c = tb->log2tab[2 * i + 1];
+    const double r = fma(z, invc, -1.0);  // |r| <= 2^-8
+    const double base = (double)k + log2c;
+    // Estrin: r*(A1 + r A2 + r^2 (A3 + r A4) + r^4 (A5 + r A6))
+    const double r2 = r * r;
+    const double a = fma(r, A[1], A[0]);
+    const double b = fma(r, A[3], A[2]);
+    const double c = fma(r, A[5], A[4]);
+    const double r4 = r2 * r2;
+    double t = fma(r2, b, a);
+    t = fma(r4, c, t);
+    return fma(r, t, base);
+}
+
+// 2^z for |z| < 1020.  relative error ~ 2e-16.
+__host__ __device__ __forceinline__ double fast_exp2_bounded(double z, const FastTables* tb) {
+    constexpr double C[6] = RRB_EXP2_POLY;
+    constexpr double kShift = 0x1.8p52 / tables::kExpN;  // rounds z to multiples of 1/128
+    double kd = z + kShift;
+    const uint64_t ki = f64_bits(kd);
+    kd -= kShift;
+    const double r = z - kd;  // |r| <= 2^-8
+    const uint64_t sbits = tb->exp2tab[ki & (tables::kExpN - 1)] + (ki << 45);
+    const double scale = bits_f64(sbits);
+    // 2^r - 1 = r*(C1 + r C2 + r^2 (C3 + r C4 + r^2 C5))
+    const double r2 = r * r;
+    const double a = fma(r, C[1], C[0]);
+    double b = fma(r, C[3], C[2]);
+    b = fma(r2, C[4], b);
+    const double t = fma(r2, b, a);
+    return fma(scale, r * t, scale);
+}
+
+// 2^z - 1 for 0 <= z (z is clamped to 64; NaN propagates).  Relative error ~3e-16 for every z,
+// including z -> 0 (no cancellation: the table holds 2^(j/128) - 1 itself).
+__host__ __device__ __forceinline__ double fast_exp2m1_nonneg(double z, const FastTables* tb) {
+    constexpr double C[6] = RRB_EXP2_POLY;
+    constexpr double kShift = 0x1.8p52 / tables::kExpN;
+    z = (z > 64.0) ? 64.0 : z;
+    double kd = z + kShift;
+    const uint64_t ki = f64_bits(kd);
+    kd -= kShift;
+    const double r = z - kd;
+    const int j = (int)(ki & (tables::kExpN - 1));
+    const double scale = bits_f64(tb->exp2tab[j] + (ki << 45));
+    const double base = ((ki & 0xFFFFFFFFULL) < (uint64_t)tables::kExpN) ? tb->exp2m1tab[j] : scale - 1.0;
+    const double r2 = r * r;
+    const double a = fma(r, C[1], C[0]);
+    double b = fma(r, C[3], C[2]);
+    b = fma(r2, C[4], b);
+    const double t = fma(r2, b, a);
+    return fma(scale, r * t, base);
+}
+
+// x^y.  Fast path for positive normal x with a comfortably finite result, libm otherwise.
+__host__ __device__ __forceinline__ double fast_pow(double x, double y, const FastTables* tb) {
+    const uint64_t ix = f64_bits(x);
+    if (ix - 0x0010000000000000ULL < 0x7FE0000000000000ULL) {  // 0 < x < inf, normal
+        const double z = y * fast_log2_normal(x, tb);
+        if (fabs(z) < 1000.0) return fast_exp2_bounded(z, tb);  // also rejects NaN
+    }
+    return pow(x, y);
+}
+
+#ifdef __CUDACC__
+// v^(-1/4) for v >= 1 finite: fp32 SFU seed refined by one third-order step and one Newton step
+// (result within ~1 ulp).  Used for the (1 + u^4)^(-0.25) terms of rrmpg/models/gr4j_model.py:117,145.
+__device__ __forceinline__ double fast_rsqrt4_ge1(double v) {
+    if (!(v < 1e30)) return pow(v, -0.25);  // inf / nan / huge: keep libm semantics
+    const float vf = (float)v;
+    double y = (double)rsqrtf(sqrtf(vf));            // ~2^-22
+    double y2 = y * y;
+    double e = fma(-v, y2 * y2, 1.0);                // 1 - v y^4
+    y = fma(y, e * fma(e, 0.15625, 0.25), y);        // y (1 + e/4 + 5 e^2/32): error ~ e^3
+    y2 = y * y;
+    e = fma(-v, y2 * y2, 1.0);
+    return fma(y * 0.25, e, y);
+}
+
+// stage the tables into shared memory (call by every thread, before a __syncthreads())
+__device__ __forceinline__ const FastTables* fastmath_tables_to_smem(unsigned char* smem_at) {
+    FastTables* dst = reinterpret_cast<FastTables*>(smem_at);
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(&d_fast_tables);
+    uint64_t* d = reinterpret_cast<uint64_t*>(dst);
+    for (int k = threadIdx.x; k < (int)(sizeof(FastTables) / 8); k += blockDim.x) d[k] = src[k];
+    return dst;
+}
+#endif
+
+constexpr size_t fastmath_smem_bytes() { return sizeof(FastTables); }
+
+}  // namespace rrb

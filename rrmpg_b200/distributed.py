@@ -1,0 +1,89 @@
+"""Multi-GPU plumbing: one process per GPU, ensembles sharded by contiguous member block.
+
+Members are independent given the forcing (the reference's member loop has no cross-iteration
+dependence, ``rrmpg/models/hbvedu.py:199-209``), so the path shards with no data-path collective:
+rank r simulates columns ``[lo_r, hi_r)`` of the ``[T, N]`` result and the only communication is
+ONE broadcast of the (small, member-independent) forcing arrays from rank 0 before the launch.
+``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the CPU tests) carries that broadcast.
+"""
+import os
+
+import numpy as np
+
+
+def env_world():
+    """(rank, local_rank, world_size) from the torchrun environment (1 process = 1 GPU)."""
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def member_block(n_members, rank, world_size):
+    """Contiguous member block ``[lo, hi)`` of ``rank``; blocks differ in size by at most one."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, rem = divmod(int(n_members), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def init_process_group(backend=None):
+    """Initialise torch.distributed from the environment; returns (rank, local_rank, world_size)."""
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def pack_forcing(series):
+    """dict of equal-length float64 [T] (or [T, L]) arrays -> one [rows, T] matrix + the layout."""
+    names = sorted(series)
+    rows, layout = [], []
+    for n in names:
+        a = np.asarray(series[n], dtype=np.float64)
+        a2 = a.reshape(a.shape[0], -1).T  # [cols, T]
+        layout.append((n, a.shape))
+        rows.append(a2)
+    return np.ascontiguousarray(np.concatenate(rows, axis=0)), layout
+
+
+def unpack_forcing(mat, layout):
+    out, r = {}, 0
+    for name, shape in layout:
+        cols = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+        block = mat[r:r + cols]
+        out[name] = (block.T.reshape(shape) if len(shape) > 1 else block[0])
+        r += cols
+    return out
+
+
+def broadcast_forcing(tensor, src=0):
+    """One collective for the whole forcing block (in place).  No-op for a single process."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(tensor, src=src)
+    return tensor
+
+
+def max_over_ranks(value, device=None):
+    """Max of a python float over all ranks (timings are reported as the slowest rank)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

@@ -1,0 +1,278 @@
+"""Batched ensemble simulations: the array-level API over the C ABI.
+
+One call here = one pass of the hot path over a whole ensemble: it replaces the reference's
+``for i in range(params.size): run_<model>(..., params[i])`` loops
+(``rrmpg/models/hbvedu.py:199-209`` and siblings) by a single library call.
+
+Two calling modes, chosen by the argument types:
+
+* **numpy** arrays: host mode.  The library uploads forcing + parameters, runs the kernel over
+  time slabs and streams finished output rows back while the next slab computes.  Outputs are
+  numpy arrays (pinned host memory when large).
+* **torch CUDA tensors** (float64, contiguous): device mode.  Nothing leaves the GPU; the work
+  is enqueued on torch's current stream and the outputs are CUDA tensors.
+
+Every function returns a dict: ``{'qsim': [T,N], <storage name>: ..., 'mse': [N]}`` (keys
+present only when requested).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_MATH = {"fast": _lib.MATH_FAST, "precise": _lib.MATH_PRECISE,
+         _lib.MATH_FAST: _lib.MATH_FAST, _lib.MATH_PRECISE: _lib.MATH_PRECISE}
+
+DEFAULT_MATH = "fast"
+
+
+def _is_torch(a):
+    return a is not None and type(a).__module__.split(".")[0] == "torch"
+
+
+def pack_params(params):
+    """Structured record array of a model ``_dtype`` (or [N,k] matrix) -> C-contiguous float64 [N,k]."""
+    if _is_torch(params):
+        return params
+    params = np.asarray(params)
+    if params.dtype.names:
+        params = np.ascontiguousarray(np.atleast_1d(params))
+        k = len(params.dtype.names)
+        if params.dtype.itemsize == 8 * k and all(params.dtype[n] == np.float64 for n in params.dtype.names):
+            return params.view(np.float64).reshape(params.size, k)  # zero-copy
+        out = np.empty((params.size, k), np.float64)
+        for j, name in enumerate(params.dtype.names):
+            out[:, j] = params[name]
+        return out
+    return np.ascontiguousarray(np.atleast_2d(params), dtype=np.float64)
+
+
+class _Call:
+    """Collects arguments of one library call in either mode."""
+
+    def __init__(self, arrays, math, device, block, slab_steps, qobs, x4_max=0.0):
+        self.torch_mode = any(_is_torch(a) for a in arrays)
+        self.opts = _lib.Opts()
+        self.opts.struct_size = C.sizeof(_lib.Opts)
+        self.opts.math = _MATH[math]
+        self.opts.block = int(block)
+        self.opts.slab_steps = int(slab_steps)
+        self.opts.x4_max = float(x4_max)
+        self.keep = []
+        if self.torch_mode:
+            import torch
+            self.torch = torch
+            devs = {a.device for a in arrays if _is_torch(a)}
+            if len(devs) != 1 or next(iter(devs)).type != "cuda":
+                raise ValueError("device mode needs every tensor on the same CUDA device")
+            self.dev = next(iter(devs))
+            self.opts.mem = _lib.MEM_DEVICE
+            self.opts.device = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+            self.opts.stream = torch.cuda.current_stream(self.dev).cuda_stream
+        else:
+            self.opts.mem = _lib.MEM_HOST
+            self.opts.device = -1 if device is None else int(device)
+        self.mse = None
+        if qobs is not None:
+            q = self.f64(qobs)
+            self.opts.qobs = _lib.ptr(q)
+            self._qobs_len = q.shape[0]
+
+    def f64(self, a, shape=None):
+        if self.torch_mode:
+            if not _is_torch(a):
+                a = self.torch.as_tensor(np.asarray(a, dtype=np.float64), device=self.dev)
+            if a.dtype != self.torch.float64:
+                raise TypeError("device mode needs float64 tensors")
+            a = a.contiguous()
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise ValueError(f"array of shape {tuple(a.shape)}, expected {tuple(shape)}")
+        self.keep.append(a)
+        return a
+
+    def i8(self, a):
+        if self.torch_mode:
+            if not _is_torch(a):
+                a = self.torch.as_tensor(np.asarray(a, dtype=np.int8), device=self.dev)
+            if a.dtype != self.torch.int8:
+                raise TypeError("device mode needs an int8 month tensor")
+            a = a.contiguous()
+        else:
+            a = np.ascontiguousarray(a, dtype=np.int8)
+        self.keep.append(a)
+        return a
+
+    def host_f64(self, a, n):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+        if a.size != n:
+            raise ValueError(f"expected {n} values, got {a.size}")
+        self.keep.append(a)
+        return a
+
+    def empty(self, shape, given=None):
+        if given is not None:
+            if tuple(given.shape) != tuple(shape):
+                raise ValueError(f"out array of shape {tuple(given.shape)}, expected {tuple(shape)}")
+            if self.torch_mode != _is_torch(given):
+                raise TypeError("out array must live where the inputs live")
+            if self.torch_mode:
+                if given.dtype != self.torch.float64 or not given.is_contiguous():
+                    raise TypeError("out tensor must be contiguous float64")
+            elif given.dtype != np.float64 or not given.flags.c_contiguous:
+                raise TypeError("out array must be C-contiguous float64")
+            return given
+        if self.torch_mode:
+            return self.torch.empty(tuple(shape), dtype=self.torch.float64, device=self.dev)
+        return _lib.host_empty(shape)
+
+    def want_mse(self, N, T):
+        if self.opts.qobs:
+            if self._qobs_len != T:
+                raise ValueError("Arrays must have the same size.")  # rrmpg/utils/metrics.py:127-128
+            self.mse = self.empty((N,))
+            self.opts.mse = _lib.ptr(self.mse)
+
+
+def _result(call, names, arrays):
+    out = {n: a for n, a in zip(names, arrays) if a is not None}
+    if call.mse is not None:
+        out["mse"] = call.mse
+    return out
+
+
+def abc(prec, initial_state, params, return_storage=False, qobs=None, want_qsim=True,
+        math=DEFAULT_MATH, device=None, block=0, slab_steps=0, out=None):
+    """ABC model ensemble (run_abcmodel, rrmpg/models/abcmodel_model.py:16-60)."""
+    P0 = pack_params(params)
+    c = _Call([prec, P0], math, device, block, slab_steps, qobs)
+    prec = c.f64(prec); P = c.f64(P0)
+    T, N = prec.shape[0], P.shape[0]
+    if P.shape[1] != 3:
+        raise ValueError("ABC parameter records have 3 fields (a, b, c)")
+    out = out or {}
+    q = c.empty((T, N), out.get("qsim")) if want_qsim else None
+    s = c.empty((T, N), out.get("storage")) if return_storage else None
+    c.want_mse(N, T)
+    _lib.check(_lib.lib().rrb_abc_simulate(_lib.ptr(prec), T, float(initial_state), _lib.ptr(P), N,
+                                           _lib.ptr(q), _lib.ptr(s), C.byref(c.opts)))
+    return _result(c, ["qsim", "storage"], [q, s])
+
+
+def hbvedu(temp, prec, month0, PE_m, T_m, inits, params, return_storage=False, qobs=None,
+           want_qsim=True, math=DEFAULT_MATH, device=None, block=0, slab_steps=0, out=None):
+    """HBV-Edu ensemble (run_hbvedu, rrmpg/models/hbvedu_model.py:16-129).
+
+    ``month0`` is the 0-based int8 month index; ``inits`` = (snow, soil, s1, s2).
+    """
+    P0 = pack_params(params)
+    c = _Call([temp, prec, month0, PE_m, T_m, P0], math, device, block, slab_steps, qobs)
+    temp = c.f64(temp); prec = c.f64(prec); month0 = c.i8(month0)
+    PE_m = c.f64(PE_m, (12,)); T_m = c.f64(T_m, (12,)); P = c.f64(P0)
+    inits = c.host_f64(inits, 4)
+    T, N = prec.shape[0], P.shape[0]
+    if temp.shape[0] != T or month0.shape[0] != T:
+        raise ValueError("temp, prec and month must have the same length")
+    if P.shape[1] != 11:
+        raise ValueError("HBVEdu parameter records have 11 fields")
+    out = out or {}
+    q = c.empty((T, N), out.get("qsim")) if want_qsim else None
+    names = ["snow", "soil", "s1", "s2"]
+    st = [c.empty((T, N), out.get(n)) for n in names] if return_storage else [None] * 4
+    c.want_mse(N, T)
+    _lib.check(_lib.lib().rrb_hbvedu_simulate(
+        _lib.ptr(temp), _lib.ptr(prec), _lib.ptr(month0), _lib.ptr(PE_m), _lib.ptr(T_m), T,
+        _lib.ptr(inits), _lib.ptr(P), N, _lib.ptr(q), *[_lib.ptr(a) for a in st], C.byref(c.opts)))
+    return _result(c, ["qsim"] + names, [q] + st)
+
+
+def _x4_hint(P, col):
+    """Largest x4 of a host parameter matrix (device tensors: let the library reduce)."""
+    if _is_torch(P) or P.shape[0] == 0:
+        return 0.0
+    return float(np.max(P[:, col]))
+
+
+def gr4j(prec, etp, s_init, r_init, params, return_storage=False, qobs=None, want_qsim=True,
+         math=DEFAULT_MATH, device=None, block=0, slab_steps=0, out=None, x4_max=0.0):
+    """GR4J ensemble (run_gr4j, rrmpg/models/gr4j_model.py:16-157); every member is simulated."""
+    P0 = pack_params(params)
+    c = _Call([prec, etp, P0], math, device, block, slab_steps, qobs, x4_max)
+    prec = c.f64(prec); etp = c.f64(etp); P = c.f64(P0)
+    T, N = prec.shape[0], P.shape[0]
+    if etp.shape[0] != T:
+        raise ValueError("prec and etp must have the same length")
+    if P.shape[1] != 4:
+        raise ValueError("GR4J parameter records have 4 fields (x1, x2, x3, x4)")
+    out = out or {}
+    q = c.empty((T, N), out.get("qsim")) if want_qsim else None
+    names = ["s_store", "r_store"]
+    st = [c.empty((T, N), out.get(n)) for n in names] if return_storage else [None] * 2
+    c.want_mse(N, T)
+    _lib.check(_lib.lib().rrb_gr4j_simulate(_lib.ptr(prec), _lib.ptr(etp), T, float(s_init), float(r_init),
+                                            _lib.ptr(P), N, _lib.ptr(q), _lib.ptr(st[0]), _lib.ptr(st[1]),
+                                            C.byref(c.opts)))
+    return _result(c, ["qsim"] + names, [q] + st)
+
+
+def cemaneige(prec, mean_temp, frac_solid, snow_pack_init, thermal_state_init, params,
+              return_storages=False, qobs=None, want_outflow=True, math=DEFAULT_MATH, device=None,
+              block=0, slab_steps=0, out=None):
+    """Cemaneige ensemble (run_cemaneige, rrmpg/models/cemaneige_model.py:16-127).
+
+    ``prec``, ``mean_temp``, ``frac_solid`` are the preprocessed [T, L] layer arrays.  ``params`` may
+    be Cemaneige records (CTG, Kf) or any record type whose first two fields are (CTG, Kf).
+    """
+    P0 = pack_params(params)
+    c = _Call([prec, mean_temp, frac_solid, P0], math, device, block, slab_steps, qobs)
+    prec = c.f64(prec); mean_temp = c.f64(mean_temp, prec.shape); frac_solid = c.f64(frac_solid, prec.shape)
+    P = c.f64(P0)
+    if prec.ndim != 2:
+        raise ValueError("layer arrays must be [T, L]")
+    (T, L), N = prec.shape, P.shape[0]
+    if P.shape[1] < 2:
+        raise ValueError("Cemaneige parameter records start with (CTG, Kf)")
+    out = out or {}
+    q = c.empty((T, N), out.get("outflow")) if want_outflow else None
+    names = ["G", "eTG"]
+    st = [c.empty((T, L, N), out.get(n)) for n in names] if return_storages else [None] * 2
+    c.want_mse(N, T)
+    _lib.check(_lib.lib().rrb_cemaneige_simulate(
+        _lib.ptr(prec), _lib.ptr(mean_temp), _lib.ptr(frac_solid), T, L, float(snow_pack_init),
+        float(thermal_state_init), _lib.ptr(P), P.shape[1], N, _lib.ptr(q), _lib.ptr(st[0]),
+        _lib.ptr(st[1]), C.byref(c.opts)))
+    return _result(c, ["outflow"] + names, [q] + st)
+
+
+def cemaneigegr4j(prec, mean_temp, etp, frac_solid, inits, params, return_storages=False, qobs=None,
+                  want_qsim=True, math=DEFAULT_MATH, device=None, block=0, slab_steps=0, out=None,
+                  x4_max=0.0):
+    """Cemaneige + GR4J ensemble (run_cemaneigegr4j, rrmpg/models/cemaneigegr4j_model.py:17-64).
+
+    ``inits`` = (snow_pack_init, thermal_state_init, s_init, r_init).
+    """
+    P0 = pack_params(params)
+    c = _Call([prec, mean_temp, etp, frac_solid, P0], math, device, block, slab_steps, qobs, x4_max)
+    prec = c.f64(prec); mean_temp = c.f64(mean_temp, prec.shape); frac_solid = c.f64(frac_solid, prec.shape)
+    etp = c.f64(etp); P = c.f64(P0)
+    inits = c.host_f64(inits, 4)
+    if prec.ndim != 2:
+        raise ValueError("layer arrays must be [T, L]")
+    (T, L), N = prec.shape, P.shape[0]
+    if etp.shape[0] != T:
+        raise ValueError("etp must have the same length as the layer arrays")
+    if P.shape[1] != 6:
+        raise ValueError("CemaneigeGR4J parameter records have 6 fields")
+    out = out or {}
+    q = c.empty((T, N), out.get("qsim")) if want_qsim else None
+    G = c.empty((T, L, N), out.get("G")) if return_storages else None
+    E = c.empty((T, L, N), out.get("eTG")) if return_storages else None
+    s = c.empty((T, N), out.get("s_store")) if return_storages else None
+    r = c.empty((T, N), out.get("r_store")) if return_storages else None
+    c.want_mse(N, T)
+    _lib.check(_lib.lib().rrb_cemaneigegr4j_simulate(
+        _lib.ptr(prec), _lib.ptr(mean_temp), _lib.ptr(etp), _lib.ptr(frac_solid), T, L, _lib.ptr(inits),
+        _lib.ptr(P), N, _lib.ptr(q), _lib.ptr(G), _lib.ptr(E), _lib.ptr(s), _lib.ptr(r), C.byref(c.opts)))
+    return _result(c, ["qsim", "G", "eTG", "s_store", "r_store"], [q, G, E, s, r])

@@ -1,0 +1,331 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors made by the live numba
+reference and against the CPU oracle on fresh seeded inputs.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import oracle
+from rrmpg_b200 import engine, synthetic
+from rrmpg_b200.models import ABCModel, HBVEdu, GR4J, Cemaneige, CemaneigeGR4J
+from rrmpg_b200.tools import monte_carlo
+from conftest import assert_bits_equal, assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+MATHS = ["fast", "precise"]
+
+
+# ------------------------------------------------------------------ reference fixtures (KATs)
+def test_fixture_hbvedu_matlab():
+    g = load_golden("fixture_hbvedu")
+    names = ['T_t', 'DD', 'FC', 'Beta', 'C', 'PWP', 'K_0', 'K_1', 'K_2', 'K_p', 'L']
+    model = HBVEdu(params=dict(zip(names, [float(v) for v in g["params"][0]])))
+    out = model.simulate(temp=g["temp"], prec=g["prec"], month=g["month"], PE_m=g["PE_m"], T_m=g["T_m"],
+                         snow_init=0, soil_init=100, s1_init=3, s2_init=10, return_storage=True)
+    # the reference's own criterion (test/test_models.py:172-174)
+    assert np.allclose((out[0] * 410 * 1000 / (24 * 60 * 60)).flatten(), g["expected"])
+    for nm, a in zip(["qsim", "snow", "soil", "s1", "s2"], out):
+        assert_close(a, g[nm], "fixture_hbvedu." + nm)
+
+
+def test_fixture_gr4j_excel():
+    g = load_golden("fixture_gr4j")
+    model = GR4J(params=dict(zip(['x1', 'x2', 'x3', 'x4'], [float(v) for v in g["params"][0]])))
+    out = model.simulate(g["prec"], g["etp"], s_init=0.6, r_init=0.7, return_storage=True)
+    assert np.allclose(out[0].flatten(), g["expected"])  # test/test_models.py:201-210
+    for nm, a in zip(["qsim", "s_store", "r_store"], out):
+        assert_close(a, g[nm], "fixture_gr4j." + nm)
+    # return_storage=False gives the same discharge
+    assert_bits_equal(model.simulate(g["prec"], g["etp"], s_init=0.6, r_init=0.7), out[0], "gr4j qsim-only")
+
+
+def test_fixture_cemaneige_excel():
+    g = load_golden("fixture_cemaneige")
+    model = Cemaneige(params={'CTG': 0.25, 'Kf': 3.74})
+    out = model.simulate(g["prec"], g["mean_temp"], g["min_temp"], g["max_temp"], met_station_height=495,
+                         altitudes=[550, 620, 700, 785, 920], return_storages=True)
+    assert np.allclose(out[0].flatten(), g["expected"])  # test/test_models.py:227-236
+    for nm, a in zip(["outflow", "G", "eTG"], out):
+        assert_bits_equal(a, g[nm], "fixture_cemaneige." + nm)
+
+
+def test_fixture_cemaneigegr4j_excel():
+    g = load_golden("fixture_cemaneigegr4j")
+    names = ['CTG', 'Kf', 'x1', 'x2', 'x3', 'x4']
+    model = CemaneigeGR4J(params=dict(zip(names, [float(v) for v in g["params"][0]])))
+    out = model.simulate(g["prec"], g["mean_temp"], g["min_temp"], g["max_temp"], g["etp"],
+                         met_station_height=495, altitudes=[550, 620, 700, 785, 920], s_init=0.6, r_init=0.7,
+                         return_storages=True)
+    assert np.allclose(out[0].flatten(), g["expected"])  # test/test_models.py:258-268
+    assert_bits_equal(out[1], g["G"], "fixture_cemaneigegr4j.G")
+    assert_bits_equal(out[2], g["eTG"], "fixture_cemaneigegr4j.eTG")
+    for nm, a in zip(["qsim", "s_store", "r_store"], (out[0], out[3], out[4])):
+        assert_close(a, g[nm], "fixture_cemaneigegr4j." + nm)
+
+
+# ------------------------------------------------------------------ numba ensembles (golden)
+@pytest.mark.parametrize("math", MATHS)
+def test_ensemble_abc(math):
+    g = load_golden("ensemble_abc")
+    r = engine.abc(g["prec"], float(g["initial_state"]), g["params"], return_storage=True, math=math)
+    assert_bits_equal(r["qsim"], g["qsim"], "abc.qsim")
+    assert_bits_equal(r["storage"], g["storage"], "abc.storage")
+
+
+@pytest.mark.parametrize("math", MATHS)
+def test_ensemble_hbvedu(math):
+    g = load_golden("ensemble_hbvedu")
+    m0 = (g["month"] - 1).astype(np.int8)
+    r = engine.hbvedu(g["temp"], g["prec"], m0, g["PE_m"], g["T_m"], g["inits"], g["params"],
+                      return_storage=True, math=math)
+    for nm in ["qsim", "snow", "soil", "s1", "s2"]:
+        assert_close(r[nm], g[nm], f"hbvedu[{math}]." + nm)
+    assert_bits_equal(r["snow"], g["snow"], "hbvedu.snow")  # the snow store has no pow: exact
+    r = engine.hbvedu(g["temp"] - 6, g["prec"], m0, g["PE_m"], g["T_m"], g["inits_cold"], g["params"],
+                      return_storage=True, math=math)
+    assert_close(r["qsim"], g["qsim_cold"], f"hbvedu[{math}].cold.qsim")
+    assert_close(r["soil"], g["soil_cold"], f"hbvedu[{math}].cold.soil")
+
+
+@pytest.mark.parametrize("math", MATHS)
+def test_ensemble_gr4j(math):
+    g = load_golden("ensemble_gr4j")
+    r = engine.gr4j(g["prec"], g["etp"], 0.6, 0.7, g["params"], return_storage=True, math=math)
+    for nm in ["qsim", "s_store", "r_store"]:
+        assert_close(r[nm], g[nm], f"gr4j[{math}]." + nm)
+    # long unit hydrographs: x4 = 3.1 / 4.5 / 7.25 / 10 / 15.5 in ONE batch and one by one
+    r = engine.gr4j(g["prec"], g["etp"], 0.3, 0.5, g["params_longuh"], return_storage=True, math=math)
+    for nm in ["qsim", "s_store", "r_store"]:
+        assert_close(r[nm], g[nm + "_longuh"], f"gr4j[{math}].longuh." + nm)
+    for i in range(g["params_longuh"].shape[0]):
+        r = engine.gr4j(g["prec"], g["etp"], 0.3, 0.5, g["params_longuh"][i:i + 1], math=math)
+        assert_close(r["qsim"][:, 0], g["qsim_longuh"][:, i], f"gr4j[{math}].longuh[{i}]")
+
+
+@pytest.mark.parametrize("math", MATHS)
+def test_ensemble_cemaneige(math):
+    g = load_golden("ensemble_cemaneige")
+    r = engine.cemaneige(g["layer_prec"], g["layer_mean_temp"], g["frac_solid"], 0.0, 0.0, g["params"],
+                         return_storages=True, math=math)
+    for nm in ["outflow", "G", "eTG"]:
+        assert_bits_equal(r[nm], g[nm], f"cemaneige[{math}]." + nm)
+    r = engine.cemaneige(g["prec"][:, None], g["mean_temp"][:, None], g["frac_solid_L1"], 12.0, -1.5,
+                         g["params"], return_storages=True, math=math)
+    for nm in ["outflow", "G", "eTG"]:
+        assert_bits_equal(r[nm], g[nm + "_L1"], f"cemaneige[{math}].L1." + nm)
+    r = engine.cemaneige(g["layer_prec_high"], g["layer_mean_temp_high"], g["frac_solid_high"], 0.0, 0.0,
+                         g["params"], math=math)
+    assert_bits_equal(r["outflow"], g["outflow_high"], f"cemaneige[{math}].high.outflow")
+
+
+@pytest.mark.parametrize("math", MATHS)
+def test_ensemble_cemaneigegr4j(math):
+    g = load_golden("ensemble_cemaneigegr4j")
+    c = load_golden("ensemble_cemaneige")
+    r = engine.cemaneigegr4j(c["layer_prec"], c["layer_mean_temp"], g["etp"], c["frac_solid"], g["inits"],
+                             g["params"], return_storages=True, math=math)
+    assert_bits_equal(r["G"], g["G"], "cemaneigegr4j.G")
+    assert_bits_equal(r["eTG"], g["eTG"], "cemaneigegr4j.eTG")
+    for nm in ["qsim", "s_store", "r_store"]:
+        assert_close(r[nm], g[nm], f"cemaneigegr4j[{math}]." + nm)
+    r = engine.cemaneigegr4j(g["prec"][:, None], g["mean_temp"][:, None], g["etp"], c["frac_solid_L1"],
+                             g["inits_L1"], g["params"], return_storages=True, math=math)
+    assert_close(r["qsim"], g["qsim_L1"], f"cemaneigegr4j[{math}].L1.qsim")
+    assert_close(r["s_store"], g["s_store_L1"], f"cemaneigegr4j[{math}].L1.s_store")
+
+
+# ------------------------------------------------------------------ drop-in models vs oracle, fresh inputs
+def _hbv_case(T, N, seed=1):
+    f = synthetic.forcing(T, seed=synthetic.SEED + seed)
+    P = synthetic.random_params(HBVEdu(), N, seed=synthetic.PARAM_SEED + seed)
+    return f, P
+
+
+@pytest.mark.parametrize("N", [1, 31, 64, 1000, 4099])
+def test_hbvedu_model_vs_oracle_ragged_sizes(N):
+    f, P = _hbv_case(1500, N)
+    q = HBVEdu().simulate(f["temp"], f["prec"], f["month"], f["PE_m"], f["T_m"], params=P, **synthetic.HBV_INITS)
+    ref = oracle.hbvedu(f["temp"], f["prec"], f["month"] - 1, f["PE_m"], f["T_m"], (0, 100, 3, 10), P)
+    assert q.shape == (1500, N)
+    assert_close(q, ref, f"hbvedu N={N}")
+
+
+@pytest.mark.parametrize("T", [1, 2, 127, 128, 129, 385])
+def test_hbvedu_short_series(T):
+    f, P = _hbv_case(T, 70, seed=3)
+    r = engine.hbvedu(f["temp"], f["prec"], f["month"] - 1, f["PE_m"], f["T_m"], (1, 100, 3, 10), P,
+                      return_storage=True)
+    ref = oracle.hbvedu(f["temp"], f["prec"], f["month"] - 1, f["PE_m"], f["T_m"], (1, 100, 3, 10), P,
+                        return_storage=True)
+    for nm, b in zip(["qsim", "snow", "soil", "s1", "s2"], ref):
+        assert_close(r[nm], b, f"hbvedu T={T} {nm}")
+
+
+def test_single_member_from_attributes_and_void():
+    f = synthetic.forcing(400)
+    m = GR4J()
+    q1 = m.simulate(f["prec"], f["etp"], s_init=0.5, r_init=0.5)
+    P = np.zeros(1, m.get_dtype())
+    for k, v in m.get_params().items():
+        P[k] = v
+    q2 = m.simulate(f["prec"], f["etp"], s_init=0.5, r_init=0.5, params=P[0])  # np.void
+    assert q1.shape == (400, 1)
+    assert_bits_equal(q1, q2, "params=None vs np.void")
+    assert_close(q1, oracle.gr4j(f["prec"], f["etp"], 0.5, 0.5, P), "gr4j single")
+
+
+def test_gr4j_multi_member_without_storage_computes_all_members():
+    """The reference returns after member 0 here (rrmpg/models/gr4j.py:178); the engine must not."""
+    f = synthetic.forcing(600)
+    P = synthetic.random_params(GR4J(), 17)
+    q = GR4J().simulate(f["prec"], f["etp"], s_init=0.6, r_init=0.7, params=P)
+    assert np.all(np.abs(q).sum(axis=0) > 0)
+    assert_close(q, oracle.gr4j(f["prec"], f["etp"], 0.6, 0.7, P), "gr4j all members")
+
+
+def test_zero_rain_gives_zero_discharge():
+    # test/test_models.py:90-92, :123-129, :195-199
+    assert np.sum(ABCModel().simulate(np.zeros(100))) == 0
+    rng = np.random.default_rng(5)
+    q = HBVEdu().simulate(temp=rng.uniform(-15, 25, 100), prec=np.zeros(100), month=rng.integers(1, 12, 100),
+                          PE_m=rng.uniform(0, 4, 12), T_m=rng.uniform(-5, 15, 12))
+    assert np.sum(q) == 0
+    q = GR4J().simulate(prec=np.zeros(100), etp=rng.uniform(0, 3, 100), s_init=0, r_init=0)
+    assert np.sum(q) == 0
+
+
+def test_cemaneige_models_vs_oracle_without_altitudes_and_layer_counts():
+    f = synthetic.forcing(900, seed=77)
+    P = synthetic.random_params(Cemaneige(), 45)
+    out = Cemaneige().simulate(f["prec"], f["temp"], f["min_temp"], f["max_temp"], met_station_height=900,
+                               snow_pack_init=3, thermal_state_init=-0.25, params=P, return_storages=True)
+    fr = oracle.calculate_solid_fraction(f["prec"][:, None], [900.0], f["temp"][:, None], f["min_temp"][:, None],
+                                         f["max_temp"][:, None])
+    ref = oracle.cemaneige(f["prec"][:, None], f["temp"][:, None], fr, 3.0, -0.25, P, return_storages=True)
+    for a, b, nm in zip(out, ref, ["outflow", "G", "eTG"]):
+        assert_bits_equal(a, b, "cemaneige no-altitudes " + nm)
+    for alts in ([600, 800], [500, 700, 900, 1100, 1300, 1600, 2100], list(range(400, 2000, 100))):
+        out = Cemaneige().simulate(f["prec"], f["temp"], f["min_temp"], f["max_temp"], met_station_height=450,
+                                   altitudes=alts, params=P, return_storages=True)
+        p = oracle.extrapolate_precipitation(f["prec"], alts, 450)
+        mn, me, mx = oracle.extrapolate_temperature(f["min_temp"], f["temp"], f["max_temp"], alts, 450)
+        fr = oracle.calculate_solid_fraction(p, alts, me, mn, mx)
+        ref = oracle.cemaneige(p, me, fr, 0.0, 0.0, P, return_storages=True)
+        for a, b, nm in zip(out, ref, ["outflow", "G", "eTG"]):
+            assert_bits_equal(a, b, f"cemaneige L={len(alts)} {nm}")
+    PC = synthetic.random_params(CemaneigeGR4J(), 33)
+    alts = [500, 700, 900]
+    out = CemaneigeGR4J().simulate(f["prec"], f["temp"], f["min_temp"], f["max_temp"], f["etp"],
+                                   met_station_height=450, altitudes=alts, s_init=0.4, r_init=0.3, params=PC,
+                                   return_storages=True)
+    p = oracle.extrapolate_precipitation(f["prec"], alts, 450)
+    mn, me, mx = oracle.extrapolate_temperature(f["min_temp"], f["temp"], f["max_temp"], alts, 450)
+    fr = oracle.calculate_solid_fraction(p, alts, me, mn, mx)
+    ref = oracle.cemaneigegr4j(p, me, f["etp"], fr, (0, 0, 0.4, 0.3), PC, return_storages=True)
+    for a, b, nm in zip(out, ref, ["qsim", "G", "eTG", "s_store", "r_store"]):
+        assert_close(a, b, "cemaneigegr4j L=3 " + nm)
+
+
+def test_too_many_layers_and_too_long_uh_fail_loudly():
+    f = synthetic.forcing(50)
+    with pytest.raises(RuntimeError, match="elevation layers"):
+        Cemaneige().simulate(f["prec"], f["temp"], f["min_temp"], f["max_temp"], met_station_height=450,
+                             altitudes=list(range(500, 500 + 17 * 50, 50)))
+    P = synthetic.random_params(GR4J(), 3)
+    P["x4"][1] = 70.0
+    with pytest.raises(RuntimeError, match="x4"):
+        GR4J().simulate(f["prec"], f["etp"], params=P)
+
+
+def test_nan_propagation_matches_oracle():
+    f = synthetic.forcing(300)
+    P = synthetic.random_params(HBVEdu(), 40)
+    P["FC"][3] = -150.0   # negative base of the pow -> NaN from the first wet step on
+    P["Beta"][7] = np.nan
+    prec = f["prec"].copy()
+    q = engine.hbvedu(f["temp"], prec, f["month"] - 1, f["PE_m"], f["T_m"], (0, 100, 3, 10), P)["qsim"]
+    ref = oracle.hbvedu(f["temp"], prec, f["month"] - 1, f["PE_m"], f["T_m"], (0, 100, 3, 10), P)
+    assert np.isnan(ref[:, 3]).any()
+    assert_close(q, ref, "hbvedu NaN members")
+
+
+# ------------------------------------------------------------------ time-slab pipeline, objective, device mode
+@pytest.mark.parametrize("slab", [1, 7, 128, 300])
+def test_time_slab_pipeline_is_bit_identical_to_one_launch(slab):
+    f, P = _hbv_case(700, 257, seed=9)
+    args = (f["temp"], f["prec"], f["month"] - 1, f["PE_m"], f["T_m"], (0, 100, 3, 10), P)
+    one = engine.hbvedu(*args, return_storage=True, slab_steps=700)
+    many = engine.hbvedu(*args, return_storage=True, slab_steps=slab)
+    for nm in one:
+        assert_bits_equal(many[nm], one[nm], f"hbvedu slab={slab} {nm}")
+    PG = synthetic.random_params(CemaneigeGR4J(), 130)
+    c = load_golden("ensemble_cemaneige")
+    etp = load_golden("ensemble_cemaneigegr4j")["etp"]
+    args = (c["layer_prec"], c["layer_mean_temp"], etp, c["frac_solid"], (0, 0, 0.6, 0.7), PG)
+    one = engine.cemaneigegr4j(*args, return_storages=True, slab_steps=1096)
+    many = engine.cemaneigegr4j(*args, return_storages=True, slab_steps=slab)
+    for nm in one:
+        assert_bits_equal(many[nm], one[nm], f"cemaneigegr4j slab={slab} {nm}")
+
+
+def test_fused_mse_matches_calc_mse_of_the_reference():
+    g = load_golden("ensemble_hbvedu")
+    m = load_golden("ensemble_hbvedu_mse")
+    r = engine.hbvedu(g["temp"], g["prec"], (g["month"] - 1).astype(np.int8), g["PE_m"], g["T_m"], g["inits"],
+                      g["params"], qobs=m["qobs"], want_qsim=False)
+    assert "qsim" not in r
+    np.testing.assert_allclose(r["mse"], m["mse"], rtol=1e-9)
+    # slab-carried accumulator
+    r2 = engine.hbvedu(g["temp"], g["prec"], (g["month"] - 1).astype(np.int8), g["PE_m"], g["T_m"], g["inits"],
+                       g["params"], qobs=m["qobs"], slab_steps=100)
+    np.testing.assert_allclose(r2["mse"], m["mse"], rtol=1e-9)
+    assert_close(r2["qsim"], g["qsim"], "qsim with objective")
+
+
+def test_monte_carlo_drop_in():
+    f = synthetic.forcing(500)
+    np.random.seed(42)
+    res = monte_carlo(ABCModel(), num=100, prec=f["prec"][:100])
+    assert res["qsim"].shape[1] == 100  # test/test_tools.py:26-29
+    np.random.seed(7)
+    qobs = f["prec"] * 0.3
+    res = monte_carlo(HBVEdu(), num=64, qobs=qobs, temp=f["temp"], prec=f["prec"], month=f["month"],
+                      PE_m=f["PE_m"], T_m=f["T_m"], soil_init=100)
+    assert set(res) == {"params", "qsim", "mse"}
+    ref = oracle.hbvedu(f["temp"], f["prec"], f["month"] - 1, f["PE_m"], f["T_m"], (0, 100, 0, 0), res["params"])
+    assert_close(res["qsim"], ref, "monte_carlo qsim")
+    np.testing.assert_allclose(res["mse"], oracle.mse_columns(qobs, ref), rtol=1e-9)
+
+
+def test_device_mode_torch_tensors():
+    import torch
+    f, P = _hbv_case(900, 513, seed=4)
+    dev = torch.device("cuda:0")
+    t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    r = engine.hbvedu(t(f["temp"]), t(f["prec"]), t(f["month"] - 1, torch.int8), t(f["PE_m"]), t(f["T_m"]),
+                      (0, 100, 3, 10), t(engine.pack_params(P)), return_storage=True)
+    assert r["qsim"].is_cuda
+    host = engine.hbvedu(f["temp"], f["prec"], f["month"] - 1, f["PE_m"], f["T_m"], (0, 100, 3, 10), P,
+                         return_storage=True)
+    torch.cuda.synchronize()
+    for nm in host:
+        assert_bits_equal(r[nm].cpu().numpy(), host[nm], "device vs host mode " + nm)
+    PG = synthetic.random_params(GR4J(), 200)
+    r = engine.gr4j(t(f["prec"]), t(f["etp"]), 0.6, 0.7, t(engine.pack_params(PG)))  # x4_max reduced on device
+    assert_close(r["qsim"].cpu().numpy(), oracle.gr4j(f["prec"], f["etp"], 0.6, 0.7, PG), "gr4j device mode")
+
+
+# ------------------------------------------------------------------ full-size, size-independent properties
+def test_full_size_hbvedu_properties():
+    """BASELINE config 2 shape (65 536 members x 14 610 steps): sampled columns against the oracle, the
+    member axis is a pure batch axis (column i does not depend on its neighbours or on N)."""
+    f = synthetic.forcing(synthetic.T_DAILY_40Y)
+    N = 65536
+    P = synthetic.random_params(HBVEdu(), N)
+    m0 = f["month"] - 1
+    q = engine.hbvedu(f["temp"], f["prec"], m0, f["PE_m"], f["T_m"], (0, 100, 3, 10), P)["qsim"]
+    assert q.shape == (synthetic.T_DAILY_40Y, N) and np.isfinite(q).all() and (q[0] == 0).all()
+    idx = np.r_[0:64, N - 64:N, np.random.default_rng(0).integers(0, N, 128)]
+    ref = oracle.hbvedu(f["temp"], f["prec"], m0, f["PE_m"], f["T_m"], (0, 100, 3, 10), P[idx])
+    assert_close(q[:, idx], ref, "hbvedu 65k sampled columns")
+    sub = engine.hbvedu(f["temp"], f["prec"], m0, f["PE_m"], f["T_m"], (0, 100, 3, 10), P[idx])["qsim"]
+    assert_bits_equal(sub, q[:, idx], "batch independence")
