@@ -360,7 +360,7 @@ static void parallel_members(int64_t N, int nthreads, member_fn fn, void *ctx)
     span_t *sp = (span_t *)malloc(sizeof(span_t) * (size_t)nthreads);
     for (int k = 0; k < nthreads; ++k) {
         sp[k].fn = fn; sp[k].ctx = ctx;
-        sp[k].lo = N * k / nthreads; sp[k].hi = N * (k + 1) / nthreads;
+        sp[k].lo = (N * k / nthreads) & ~(int64_t)7; sp[k].hi = (k + 1 == nthreads) ? N : ((N * (k + 1) / nthreads) & ~(int64_t)7);
         pthread_create(&th[k], NULL, span_main, &sp[k]);
     }
     for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
@@ -373,12 +373,36 @@ typedef struct {
     double *o0, *o1, *o2, *o3, *o4; int rc;
 } bctx_t;
 
+/* Members are computed MB at a time into contiguous thread-local series and then written to
+ * the [rows, N] result as MB consecutive doubles per row: one cache line per row instead of
+ * one strided store per member-timestep (the reference's `qsim[:, i] = ...` column scatter,
+ * rrmpg/models/hbvedu.py:202, pays that stride; this baseline does not). */
+#define MB 8
+static void scatter_rows(const double *local, int64_t rows, int64_t nb, double *dst, int64_t N, int64_t i0)
+{
+    if (!dst) return;
+    for (int64_t r = 0; r < rows; ++r)
+        for (int64_t b = 0; b < nb; ++b) dst[r * N + i0 + b] = local[b * rows + r];
+}
+static double *local_alloc(int64_t rows, int nbuf)
+{
+    return (double *)malloc(sizeof(double) * (size_t)(rows > 0 ? rows : 1) * MB * (size_t)nbuf);
+}
+
 static void abc_span(int64_t lo, int64_t hi, void *v)
 {
     bctx_t *c = (bctx_t *)v;
-    for (int64_t i = lo; i < hi; ++i)
-        oracle_abc(c->a0, c->T, c->inits[0], c->params + 3 * i, c->o0 + i, c->N,
-                   c->o1 ? c->o1 + i : NULL, c->N);
+    const int64_t T = c->T;
+    double *buf = local_alloc(T, 2), *q = buf, *s = buf + MB * T;
+    for (int64_t i0 = lo; i0 < hi; i0 += MB) {
+        const int64_t nb = (hi - i0 < MB) ? hi - i0 : MB;
+        for (int64_t b = 0; b < nb; ++b)
+            oracle_abc(c->a0, T, c->inits[0], c->params + 3 * (i0 + b), q + b * T, 1,
+                       c->o1 ? s + b * T : NULL, 1);
+        scatter_rows(q, T, nb, c->o0, c->N, i0);
+        scatter_rows(s, T, nb, c->o1, c->N, i0);
+    }
+    free(buf);
 }
 void oracle_abc_batch(const double *prec, int64_t T, double s0, const double *params, int64_t N,
                       double *qsim, double *storage, int nthreads)
@@ -391,11 +415,24 @@ void oracle_abc_batch(const double *prec, int64_t T, double s0, const double *pa
 static void hbv_span(int64_t lo, int64_t hi, void *v)
 {
     bctx_t *c = (bctx_t *)v;
-    for (int64_t i = lo; i < hi; ++i)
-        oracle_hbvedu(c->a0, c->a1, c->m, c->a2, c->a3, c->T, c->inits[0], c->inits[1],
-                      c->inits[2], c->inits[3], c->params + 11 * i, c->o0 + i, c->N,
-                      c->o1 ? c->o1 + i : NULL, c->o2 ? c->o2 + i : NULL,
-                      c->o3 ? c->o3 + i : NULL, c->o4 ? c->o4 + i : NULL);
+    const int64_t T = c->T;
+    double *buf = local_alloc(T, 5);
+    double *o[5];
+    for (int k = 0; k < 5; ++k) o[k] = buf + (int64_t)k * MB * T;
+    for (int64_t i0 = lo; i0 < hi; i0 += MB) {
+        const int64_t nb = (hi - i0 < MB) ? hi - i0 : MB;
+        for (int64_t b = 0; b < nb; ++b)
+            oracle_hbvedu(c->a0, c->a1, c->m, c->a2, c->a3, T, c->inits[0], c->inits[1],
+                          c->inits[2], c->inits[3], c->params + 11 * (i0 + b), o[0] + b * T, 1,
+                          c->o1 ? o[1] + b * T : NULL, c->o1 ? o[2] + b * T : NULL,
+                          c->o1 ? o[3] + b * T : NULL, c->o1 ? o[4] + b * T : NULL);
+        scatter_rows(o[0], T, nb, c->o0, c->N, i0);
+        scatter_rows(o[1], T, nb, c->o1, c->N, i0);
+        scatter_rows(o[2], T, nb, c->o2, c->N, i0);
+        scatter_rows(o[3], T, nb, c->o3, c->N, i0);
+        scatter_rows(o[4], T, nb, c->o4, c->N, i0);
+    }
+    free(buf);
 }
 void oracle_hbvedu_batch(const double *temp, const double *prec, const int8_t *month,
                          const double *PE_m, const double *T_m, int64_t T, const double *inits,
@@ -411,11 +448,21 @@ void oracle_hbvedu_batch(const double *temp, const double *prec, const int8_t *m
 static void gr4j_span(int64_t lo, int64_t hi, void *v)
 {
     bctx_t *c = (bctx_t *)v;
-    for (int64_t i = lo; i < hi; ++i) {
-        int r = oracle_gr4j(c->a0, c->a1, c->T, c->inits[0], c->inits[1], c->params + 4 * i,
-                            c->o0 + i, c->N, c->o1 ? c->o1 + i : NULL, c->o2 ? c->o2 + i : NULL);
-        if (r) __atomic_store_n(&c->rc, r, __ATOMIC_RELAXED);
+    const int64_t T = c->T;
+    double *buf = local_alloc(T, 3);
+    double *q = buf, *s = buf + MB * T, *r = buf + 2 * MB * T;
+    for (int64_t i0 = lo; i0 < hi; i0 += MB) {
+        const int64_t nb = (hi - i0 < MB) ? hi - i0 : MB;
+        for (int64_t b = 0; b < nb; ++b) {
+            int rc = oracle_gr4j(c->a0, c->a1, T, c->inits[0], c->inits[1], c->params + 4 * (i0 + b),
+                                 q + b * T, 1, c->o1 ? s + b * T : NULL, c->o1 ? r + b * T : NULL);
+            if (rc) __atomic_store_n(&c->rc, rc, __ATOMIC_RELAXED);
+        }
+        scatter_rows(q, T, nb, c->o0, c->N, i0);
+        scatter_rows(s, T, nb, c->o1, c->N, i0);
+        scatter_rows(r, T, nb, c->o2, c->N, i0);
     }
+    free(buf);
 }
 int oracle_gr4j_batch(const double *prec, const double *etp, int64_t T, double s_init, double r_init,
                       const double *params, int64_t N, double *qsim, double *s_o, double *r_o,
@@ -432,12 +479,20 @@ int oracle_gr4j_batch(const double *prec, const double *etp, int64_t T, double s
 static void cema_span(int64_t lo, int64_t hi, void *v)
 {
     bctx_t *c = (bctx_t *)v;
-    double *lw = (double *)malloc(sizeof(double) * (size_t)(c->T * c->L > 0 ? c->T * c->L : 1));
-    for (int64_t i = lo; i < hi; ++i)
-        oracle_cemaneige(c->a0, c->a1, c->a2, c->T, c->L, c->inits[0], c->inits[1],
-                         c->params + c->pstride * i, lw, c->o0 + i, c->N,
-                         c->o1 ? c->o1 + i : NULL, c->o2 ? c->o2 + i : NULL, c->N);
-    free(lw);
+    const int64_t T = c->T, L = c->L, TL = T * L;
+    double *lw = (double *)malloc(sizeof(double) * (size_t)(TL > 0 ? TL : 1));
+    double *q = local_alloc(T, 1), *st = local_alloc(TL, 2), *G = st, *E = st + MB * TL;
+    for (int64_t i0 = lo; i0 < hi; i0 += MB) {
+        const int64_t nb = (hi - i0 < MB) ? hi - i0 : MB;
+        for (int64_t b = 0; b < nb; ++b)
+            oracle_cemaneige(c->a0, c->a1, c->a2, T, L, c->inits[0], c->inits[1],
+                             c->params + c->pstride * (i0 + b), lw, q + b * T, 1,
+                             c->o1 ? G + b * TL : NULL, c->o1 ? E + b * TL : NULL, 1);
+        scatter_rows(q, T, nb, c->o0, c->N, i0);
+        scatter_rows(G, TL, nb, c->o1, c->N, i0);
+        scatter_rows(E, TL, nb, c->o2, c->N, i0);
+    }
+    free(lw); free(q); free(st);
 }
 void oracle_cemaneige_batch(const double *prec, const double *mean_temp, const double *frac,
                             int64_t T, int64_t L, double g0, double e0, const double *params,
@@ -454,17 +509,28 @@ void oracle_cemaneige_batch(const double *prec, const double *mean_temp, const d
 static void cg_span(int64_t lo, int64_t hi, void *v)
 {
     bctx_t *c = (bctx_t *)v;
-    double *lw = (double *)malloc(sizeof(double) * (size_t)(c->T * c->L > 0 ? c->T * c->L : 1));
-    double *liq = (double *)malloc(sizeof(double) * (size_t)(c->T > 0 ? c->T : 1));
-    for (int64_t i = lo; i < hi; ++i) {
-        int r = oracle_cemaneigegr4j(c->a0, c->a1, c->a3, c->a2, c->T, c->L, c->inits[0],
-                                     c->inits[1], c->inits[2], c->inits[3], c->params + 6 * i, lw,
-                                     liq, c->o0 + i, c->N, c->o1 ? c->o1 + i : NULL,
-                                     c->o2 ? c->o2 + i : NULL, c->N, c->o3 ? c->o3 + i : NULL,
-                                     c->o4 ? c->o4 + i : NULL);
-        if (r) __atomic_store_n(&c->rc, r, __ATOMIC_RELAXED);
+    const int64_t T = c->T, L = c->L, TL = T * L;
+    double *lw = (double *)malloc(sizeof(double) * (size_t)(TL > 0 ? TL : 1));
+    double *liq = (double *)malloc(sizeof(double) * (size_t)(T > 0 ? T : 1));
+    double *buf = local_alloc(T, 3), *st = local_alloc(TL, 2);
+    double *q = buf, *s = buf + MB * T, *r = buf + 2 * MB * T, *G = st, *E = st + MB * TL;
+    for (int64_t i0 = lo; i0 < hi; i0 += MB) {
+        const int64_t nb = (hi - i0 < MB) ? hi - i0 : MB;
+        for (int64_t b = 0; b < nb; ++b) {
+            int rc = oracle_cemaneigegr4j(c->a0, c->a1, c->a3, c->a2, T, L, c->inits[0], c->inits[1],
+                                          c->inits[2], c->inits[3], c->params + 6 * (i0 + b), lw, liq,
+                                          q + b * T, 1, c->o1 ? G + b * TL : NULL,
+                                          c->o1 ? E + b * TL : NULL, 1, c->o1 ? s + b * T : NULL,
+                                          c->o1 ? r + b * T : NULL);
+            if (rc) __atomic_store_n(&c->rc, rc, __ATOMIC_RELAXED);
+        }
+        scatter_rows(q, T, nb, c->o0, c->N, i0);
+        scatter_rows(G, TL, nb, c->o1, c->N, i0);
+        scatter_rows(E, TL, nb, c->o2, c->N, i0);
+        scatter_rows(s, T, nb, c->o3, c->N, i0);
+        scatter_rows(r, T, nb, c->o4, c->N, i0);
     }
-    free(lw); free(liq);
+    free(lw); free(liq); free(buf); free(st);
 }
 int oracle_cemaneigegr4j_batch(const double *prec, const double *mean_temp, const double *etp,
                                const double *frac, int64_t T, int64_t L, const double *inits,
