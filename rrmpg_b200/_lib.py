@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librrmpg_b200.so")
+LIB_PATH = os.environ.get("RRMPG_B200_LIB", os.path.join(_HERE, "librrmpg_b200.so"))  # override: kernel experiments
 
 RRB_OK, RRB_EINVAL, RRB_ECUDA, RRB_EUNSUPPORTED, RRB_ENOMEM = range(5)
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -546,7 +546,7 @@ int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* mo
     memcpy(in4, inits, sizeof(in4));  // inits is host memory in both modes
     void* F;
     if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, kHbvTT) * kHbvR, &F))) return rc;
-    RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.s));
+    RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.o.math, P.s));
     Job job;
     job.T = T; job.N = N;
     job.outs = {{qsim, N}, {snow, N}, {soil, N}, {s1, N}, {s2, N}};

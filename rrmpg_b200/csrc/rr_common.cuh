@@ -70,9 +70,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // streaming (evict-first) stores of the output rows
 __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 
-// numba's lowering of Python max(0, x) / min(a, b) on floats (oracle/rr_oracle.c header)
-__device__ __forceinline__ double nb_max0(double x) { return (x > 0.0) ? x : 0.0; }
-__device__ __forceinline__ double nb_min(double a, double b) { return (b < a) ? b : a; }
+// numba's lowering of Python max(0, x) / min(a, b) on floats (oracle/rr_oracle.c header):
+// max(0, x) = (x > 0) ? x : 0.0 (so max(0, NaN) = 0), min(a, b) = (b < a) ? b : a.
+// Written as setp + selp so they cost one DSETP and two SELs; the C++ ternary is pattern-matched by
+// the compiler into a DSETP.MAX + NaN fix-up sequence of six instructions.
+__device__ __forceinline__ double nb_max0(double x) {
+#ifdef RRB_X_NOMAXASM
+    return (x > 0.0) ? x : 0.0;
+#endif
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, 0d0000000000000000;\n\t"
+        "selp.f64 %0, %1, 0d0000000000000000, p;\n\t}"
+        : "=d"(r)
+        : "d"(x));
+    return r;
+}
+__device__ __forceinline__ double nb_min(double a, double b) {
+#ifdef RRB_X_NOMAXASM
+    return (b < a) ? b : a;
+#endif
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %2, %1;\n\tselp.f64 %0, %2, %1, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
 
 // ----------------------------------------------------------------------------------------
 // Forcing tile pipeline.
@@ -121,6 +141,179 @@ __device__ __forceinline__ void stream_forcing(const double* __restrict__ F, int
             for (int tt = 0; tt < TT; ++tt) step(t0 + tt, tile + tt * R);
         } else {
             for (int tt = lo; tt < hi; ++tt) step(t0 + tt, tile + tt * R);
+        }
+        __syncthreads();  // every thread is done reading this stage
+        if (threadIdx.x == 0 && k + kStages < k_end) {
+            fence_proxy_async_smem();
+            mbar_arrive_expect_tx(&full[stage], kTileBytes);
+            tma_load_1d(tiles + (size_t)stage * TT * R, F + (size_t)(k + kStages) * TT * R, kTileBytes,
+                        &full[stage]);
+        }
+        if (++stage == kStages) {
+            stage = 0;
+            parity ^= 1u;
+        }
+    }
+}
+
+// explicit shared-window loads (32-bit shared address computed once; a generic pointer would make
+// the compiler re-derive the window base -- S2UR SR_CgaCtaId + ULEA -- at every use)
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// ----------------------------------------------------------------------------------------
+// Forcing tile pipeline, register-staged variant.  FV is a struct of the R forcing values of one
+// timestep with `static FV load(uint32_t shared_addr)`; the values of step t+1 are fetched from
+// shared memory while step t computes, so the ~30-cycle LDS latency never sits in front of the
+// recurrence.  step(t, fv) is called for every t in [t_begin, t_end), in order.
+// ----------------------------------------------------------------------------------------
+template <int R, int TT, class FV, class Step>
+__device__ __forceinline__ void stream_forcing_regs(const double* __restrict__ F, int64_t t_begin, int64_t t_end,
+                                                    Step&& step) {
+    extern __shared__ __align__(128) unsigned char rrb_smem[];
+    double* tiles = reinterpret_cast<double*>(rrb_smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(rrb_smem + sizeof(double) * kStages * TT * R);
+    constexpr uint32_t kTileBytes = TT * R * sizeof(double);
+    constexpr uint32_t kRowBytes = R * sizeof(double);
+    static_assert(kTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+    if (t_end <= t_begin) return;
+    const int64_t k_begin = t_begin / TT;
+    const int64_t k_end = (t_end + TT - 1) / TT;
+    const uint32_t tiles_addr = smem_u32(tiles);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            const int64_t k = k_begin + s;
+            if (k < k_end) {
+                mbar_arrive_expect_tx(&full[s], kTileBytes);
+                tma_load_1d(tiles + (size_t)s * TT * R, F + (size_t)k * TT * R, kTileBytes, &full[s]);
+            }
+        }
+    }
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int64_t k = k_begin; k < k_end; ++k) {
+        mbar_wait(&full[stage], parity);
+        const uint32_t base = tiles_addr + (uint32_t)stage * kTileBytes;
+        const int64_t t0 = k * TT;
+        const int lo = (int)((t_begin > t0) ? (t_begin - t0) : 0);
+        const int hi = (int)((t_end < t0 + TT) ? (t_end - t0) : TT);
+        FV nxt = FV::load(base + (uint32_t)lo * kRowBytes);
+        if (lo == 0 && hi == TT) {
+#pragma unroll 4
+            for (int tt = 0; tt < TT; ++tt) {
+                const FV cur = nxt;
+                nxt = FV::load(base + (uint32_t)((tt + 1 < TT) ? tt + 1 : tt) * kRowBytes);
+                step(t0 + tt, cur);
+            }
+        } else {
+            for (int tt = lo; tt < hi; ++tt) {
+                const FV cur = nxt;
+                nxt = FV::load(base + (uint32_t)((tt + 1 < hi) ? tt + 1 : tt) * kRowBytes);
+                step(t0 + tt, cur);
+            }
+        }
+        __syncthreads();  // every thread is done reading this stage
+        if (threadIdx.x == 0 && k + kStages < k_end) {
+            fence_proxy_async_smem();
+            mbar_arrive_expect_tx(&full[stage], kTileBytes);
+            tma_load_1d(tiles + (size_t)stage * TT * R, F + (size_t)(k + kStages) * TT * R, kTileBytes,
+                        &full[stage]);
+        }
+        if (++stage == kStages) {
+            stage = 0;
+            parity ^= 1u;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Forcing tile pipeline, grouped variant.  group(ic<G>, t0, fv[G]) is called for G consecutive
+// timesteps at a time (tile rows aligned to G), group(ic<1>, t, fv[1]) for the ragged steps at the
+// edges of a time slab.  A model can then run the part of its step that does not hang on the long
+// recurrence for all G steps first (high ILP), and the dependent chains afterwards.
+// ----------------------------------------------------------------------------------------
+template <int V>
+struct ic {
+    static constexpr int value = V;
+};
+
+template <int R, int TT, int G, class FV, class Group>
+__device__ __forceinline__ void stream_forcing_grouped(const double* __restrict__ F, int64_t t_begin, int64_t t_end,
+                                                       Group&& group) {
+    static_assert(TT % G == 0, "tiles hold whole groups");
+    extern __shared__ __align__(128) unsigned char rrb_smem[];
+    double* tiles = reinterpret_cast<double*>(rrb_smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(rrb_smem + sizeof(double) * kStages * TT * R);
+    constexpr uint32_t kTileBytes = TT * R * sizeof(double);
+    constexpr uint32_t kRowBytes = R * sizeof(double);
+    static_assert(kTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+    if (t_end <= t_begin) return;
+    const int64_t k_begin = t_begin / TT;
+    const int64_t k_end = (t_end + TT - 1) / TT;
+    uint32_t tiles_addr = smem_u32(tiles);
+    asm volatile("" : "+r"(tiles_addr));  // opaque: keep it in a register instead of re-deriving it
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            const int64_t k = k_begin + s;
+            if (k < k_end) {
+                mbar_arrive_expect_tx(&full[s], kTileBytes);
+                tma_load_1d(tiles + (size_t)s * TT * R, F + (size_t)k * TT * R, kTileBytes, &full[s]);
+            }
+        }
+    }
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int64_t k = k_begin; k < k_end; ++k) {
+        mbar_wait(&full[stage], parity);
+        const uint32_t base = tiles_addr + (uint32_t)stage * kTileBytes;
+        const int64_t t0 = k * TT;
+        const int lo = (int)((t_begin > t0) ? (t_begin - t0) : 0);
+        const int hi = (int)((t_end < t0 + TT) ? (t_end - t0) : TT);
+        int tt = lo;
+        for (; tt < hi && (tt % G) != 0; ++tt) {  // ragged head
+            FV f1[1] = {FV::load(base + (uint32_t)tt * kRowBytes)};
+            group(ic<1>{}, t0 + tt, f1);
+        }
+        if (tt + G <= hi) {
+            FV nxt[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) nxt[g] = FV::load(base + (uint32_t)(tt + g) * kRowBytes);
+            for (; tt + G <= hi; tt += G) {
+                FV cur[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) cur[g] = nxt[g];
+                // prefetch the next group (clamped inside the tile; a repeated row is never used)
+                const int nt = (tt + 2 * G <= TT) ? tt + G : tt;
+#pragma unroll
+                for (int g = 0; g < G; ++g) nxt[g] = FV::load(base + (uint32_t)(nt + g) * kRowBytes);
+                group(ic<G>{}, t0 + tt, cur);
+            }
+        }
+        for (; tt < hi; ++tt) {  // ragged tail
+            FV f1[1] = {FV::load(base + (uint32_t)tt * kRowBytes)};
+            group(ic<1>{}, t0 + tt, f1);
         }
         __syncthreads();  // every thread is done reading this stage
         if (threadIdx.x == 0 && k + kStages < k_end) {

@@ -5,14 +5,18 @@
 // Packed forcing per timestep (member independent): F[t] = { temp, prec, dT, PEm } with
 //   dT  = temp[t] - T_m[month[t]]   (the inner subtraction of hbvedu_model.py:102, bit-identical)
 //   PEm = PE_m[month[t]]
+// (FAST packs dT*PEm instead of dT: pe = (1 + C dT) PEm = fma(C, dT*PEm, PEm) is then one instruction.)
 // Per member: 4 stores (snow, soil, s1, s2) and 11 parameters in registers.
 //
 // MATH = PRECISE: IEEE divisions, CUDA libm pow (<= 2 ulp from glibc's), no contraction: every
 //                 operation of the reference in the reference's order.
-// MATH = FAST   : same recurrence, reciprocals of FC / PWP hoisted, table-driven pow
-//                 (rr_math.cuh, ~1e-15 relative), and the pow skipped for warps whose members all
-//                 have liquid_water == 0 (then prec_eff = 0 * finite = 0 exactly).  Discharge
-//                 stays within rtol 1e-10 of the reference (tests/test_parity_gpu.py).
+// MATH = FAST   : same recurrence with the fp64 instruction count cut ~4x: reciprocals of FC / PWP and
+//                 the linear-store coefficients hoisted, explicit FMAs, table-driven pow (rr_math.cuh,
+//                 ~1e-15 relative), and the pow skipped for warps whose members all have
+//                 liquid_water == 0 (then prec_eff = 0 * finite = +0 exactly as in the reference).
+//                 Discharge stays within rtol 1e-10 of the reference (tests/test_parity_gpu.py).
+// Both: branch-free snow routine, forcing of step t+1 prefetched into registers during step t,
+//       running output pointers, t = 0 peeled out of the time loop.
 #include "rr_common.cuh"
 #include "rr_kernels.h"
 #include "rr_math.cuh"
@@ -21,7 +25,8 @@ namespace rrb {
 
 __global__ void hbv_pack_kernel(const double* __restrict__ temp, const double* __restrict__ prec,
                                 const int8_t* __restrict__ month0, const double* __restrict__ PE_m,
-                                const double* __restrict__ T_m, int64_t T, int64_t Tpad, double* __restrict__ F) {
+                                const double* __restrict__ T_m, int64_t T, int64_t Tpad, int fast,
+                                double* __restrict__ F) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= Tpad) return;
     double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -31,14 +36,16 @@ __global__ void hbv_pack_kernel(const double* __restrict__ temp, const double* _
         v.y = prec[t];
         v.z = temp[t] - T_m[m];
         v.w = PE_m[m];
+        if (fast) v.z = v.z * v.w;
     }
     reinterpret_cast<double4*>(F)[t] = v;
 }
 
 cudaError_t pack_hbvedu(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
-                        const double* T_m, int64_t T, double* F, cudaStream_t s) {
+                        const double* T_m, int64_t T, double* F, int math, cudaStream_t s) {
     int64_t Tpad = padded_steps(T, kHbvTT);
-    hbv_pack_kernel<<<(unsigned)((Tpad + 255) / 256), 256, 0, s>>>(temp, prec, month0, PE_m, T_m, T, Tpad, F);
+    hbv_pack_kernel<<<(unsigned)((Tpad + 255) / 256), 256, 0, s>>>(temp, prec, month0, PE_m, T_m, T, Tpad,
+                                                                   math == RRB_MATH_FAST_, F);
     return cudaGetLastError();
 }
 
@@ -46,81 +53,98 @@ struct HbvOut {
     double *qsim, *snow, *soil, *s1, *s2;
 };
 
-template <int MATH, bool STORAGE, bool OBJ>
-__global__ void hbv_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
-                           const double* __restrict__ params, int64_t N, HbvOut out, Slab slab,
-                           Objective obj) {
+struct HbvF {  // forcing of one timestep
+    double temp, prec, dT, PEm;
+    static __device__ __forceinline__ HbvF load(uint32_t addr) {
+        const double2 a = lds_f64x2(addr), b = lds_f64x2(addr + 16);
+        return HbvF{a.x, a.y, b.x, b.y};
+    }
+};
+
+// rare operands (soil/FC outside [2^-15, 2^15), |Beta| >= 32, FC <= 0, non-finite values): the reference's
+// own operations, out of line so they cost the time loop one predicated branch
+__device__ __noinline__ double hbv_slow_pow(double soil, double FC, double Beta) { return pow(soil / FC, Beta); }
+
+// ------------------------------------------------------------------------------------------------
+// PRECISE: every operation of the reference, in the reference's order.
+// ------------------------------------------------------------------------------------------------
+template <bool WRITEQ, bool STORAGE, bool OBJ>
+__global__ void hbv_precise_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
+                                   const double* __restrict__ params, int64_t N, HbvOut out, Slab slab,
+                                   Objective obj) {
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const bool active = gi < N;
-    const int64_t i = active ? gi : N - 1;
+    // threads past the end of the ensemble recompute member N-1 and store the same values to the same
+    // addresses: no predicate lives in the time loop
+    const int64_t i = gi < N ? gi : N - 1;
     // record order = HBVEdu._dtype (rrmpg/models/hbvedu.py:63-66)
     const double* p = params + 11 * i;
     const double T_t = p[0], DD = p[1], FC = p[2], Beta = p[3], C = p[4], PWP = p[5];
     const double K_0 = p[6], K_1 = p[7], K_2 = p[8], K_p = p[9], L = p[10];
-    const double inv_FC = 1.0 / FC, inv_PWP = 1.0 / PWP;  // FAST only
 
     double snow = snow0, soil = soil0, s1 = s10, s2 = s20;  // hbvedu_model.py:78-81
     double acc = 0.0;
+    int64_t t_first = slab.t_begin;
+    int64_t off = i + (slab.t_begin - slab.row0) * N;  // row r of the buffers = timestep row0 + r
     if (slab.t_begin > 0) {
         snow = slab.state[0 * N + i];
         soil = slab.state[1 * N + i];
         s1 = slab.state[2 * N + i];
         s2 = slab.state[3 * N + i];
         if (OBJ) acc = slab.state[4 * N + i];
-    }
-    const int64_t off = i - slab.row0 * N;
-    double* q_o = out.qsim ? out.qsim + off : nullptr;
-
-    extern __shared__ __align__(128) unsigned char rrb_smem[];
-    const FastTables* tb = nullptr;
-    if (MATH == RRB_MATH_FAST_) tb = fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<kHbvR, kHbvTT>());
-
-    stream_forcing<kHbvR, kHbvTT>(F, slab.t_begin, slab.t_end, [&](int64_t t, const double* f) {
-        double qv = 0.0;
-        if (t > 0) {  // hbvedu_model.py:84 -- the loop starts at t = 1
-            const double2 f01 = *reinterpret_cast<const double2*>(f);
-            const double2 f23 = *reinterpret_cast<const double2*>(f + 2);
-            const double temp = f01.x, prec = f01.y, dT = f23.x, PEm = f23.y;
-            double snow_new, liquid;
-            if (temp < T_t) {  // :87
-                snow_new = snow + prec;  // :89
-                liquid = 0.0;            // :91
-            } else {
-                const double m = DD * (temp - T_t);
-                snow_new = nb_max0(snow - m);    // :94
-                liquid = prec + nb_min(snow, m);  // :96
-            }
-            double prec_eff, ea;
-            const double pe = (1 + C * dT) * PEm;  // :102
-            if (MATH == RRB_MATH_FAST_) {
-                const double x = soil * inv_FC;
-                // liquid == 0 and a finite positive power  =>  prec_eff = +0 exactly as in the reference
-                const bool need_pow = !(liquid == 0.0 && x > 0x1p-16 && x < 0x1p16 && fabs(Beta) < 32.0);
-                prec_eff = 0.0;
-                if (need_pow) prec_eff = liquid * fast_pow(x, Beta, tb);
-                ea = (soil > PWP) ? pe : pe * (soil * inv_PWP);
-            } else {
-                prec_eff = liquid * pow(soil / FC, Beta);        // :99
-                ea = (soil > PWP) ? pe : pe * (soil / PWP);      // :105-108
-            }
-            const double soil_new = soil + liquid - prec_eff - ea;  // :111
-            const double over = nb_max0(s1 - L);
-            const double s1_new = s1 + prec_eff - over * K_0 - s1 * K_1 - s1 * K_p;  // :114-118
-            const double s2_new = s2 + s1 * K_p - s2 * K_2;                            // :121-123
-            qv = over * K_0 + s1_new * K_1 + s2_new * K_2;                             // :125-127
-            snow = snow_new;
-            soil = soil_new;
-            s1 = s1_new;
-            s2 = s2_new;
+    } else {
+        // t = 0 is not simulated (the reference loop starts at 1, hbvedu_model.py:84): qsim[0] = 0 and the
+        // storages hold the initial states
+        if (WRITEQ) st_stream(out.qsim + off, 0.0);
+        if (STORAGE) {
+            st_stream(out.snow + off, snow);
+            st_stream(out.soil + off, soil);
+            st_stream(out.s1 + off, s1);
+            st_stream(out.s2 + off, s2);
         }
-        if (active) {
-            if (q_o) st_stream(q_o + t * N, qv);
-            if (STORAGE) {
-                st_stream(out.snow + off + t * N, snow);
-                st_stream(out.soil + off + t * N, soil);
-                st_stream(out.s1 + off + t * N, s1);
-                st_stream(out.s2 + off + t * N, s2);
-            }
+        if (OBJ) {
+            const double d = obj.qobs[0];
+            acc = d * d;
+        }
+        off += N;
+        t_first = 1;
+    }
+    double* q_o = WRITEQ ? out.qsim + off : nullptr;
+    double* snow_o = STORAGE ? out.snow + off : nullptr;
+    double* soil_o = STORAGE ? out.soil + off : nullptr;
+    double* s1_o = STORAGE ? out.s1 + off : nullptr;
+    double* s2_o = STORAGE ? out.s2 + off : nullptr;
+
+    stream_forcing_regs<kHbvR, kHbvTT, HbvF>(F, t_first, slab.t_end, [&](int64_t t, const HbvF& f) {
+        // snow routine, both branches evaluated and selected (hbvedu_model.py:87-96)
+        const bool cold = f.temp < T_t;
+        const double m = DD * (f.temp - T_t);
+        const double snow_new = cold ? snow + f.prec : nb_max0(snow - m);
+        const double liquid = cold ? 0.0 : f.prec + nb_min(snow, m);
+        const double prec_eff = liquid * pow(soil / FC, Beta);              // :99
+        const double pe = (1 + C * f.dT) * f.PEm;                           // :102
+        const double ea = (soil > PWP) ? pe : pe * (soil / PWP);            // :105-108
+        const double soil_new = soil + liquid - prec_eff - ea;              // :111
+        const double over = nb_max0(s1 - L);
+        const double s1_new = s1 + prec_eff - over * K_0 - s1 * K_1 - s1 * K_p;  // :114-118
+        const double s2_new = s2 + s1 * K_p - s2 * K_2;                     // :121-123
+        const double qv = over * K_0 + s1_new * K_1 + s2_new * K_2;         // :125-127
+        snow = snow_new;
+        soil = soil_new;
+        s1 = s1_new;
+        s2 = s2_new;
+        if (WRITEQ) {
+            st_stream(q_o, qv);
+            q_o += N;
+        }
+        if (STORAGE) {
+            st_stream(snow_o, snow);
+            st_stream(soil_o, soil);
+            st_stream(s1_o, s1);
+            st_stream(s2_o, s2);
+            snow_o += N;
+            soil_o += N;
+            s1_o += N;
+            s2_o += N;
         }
         if (OBJ) {
             const double d = obj.qobs[t] - qv;
@@ -128,7 +152,168 @@ __global__ void hbv_kernel(const double* __restrict__ F, double snow0, double so
         }
     });
 
-    if (active) {
+    if (gi < N) {
+        if (slab.save_state) {
+            slab.state[0 * N + i] = snow;
+            slab.state[1 * N + i] = soil;
+            slab.state[2 * N + i] = s1;
+            slab.state[3 * N + i] = s2;
+            if (OBJ) slab.state[4 * N + i] = acc;
+        }
+        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i] = acc / (double)obj.T;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST: the same recurrence reorganised for the fp64 pipe and for the few warps per scheduler that a
+// 65 536-member ensemble leaves (one thread per member = 3.5 warps per SM sub-partition).
+//   A(t)  snow routine + potential evapotranspiration: needs forcing[t], snow[t-1] and parameters only
+//   B(t)  soil moisture (the pow), response routine, discharge: the long dependent chain
+// Timesteps are processed in groups of G: first A for the whole group (independent work, high ILP),
+// then one warp vote per step ("does any member have liquid water?", known without touching the soil
+// chain), then the B chains, each either with or without the pow.
+// ------------------------------------------------------------------------------------------------
+#ifndef RRB_HBV_GROUP
+#define RRB_HBV_GROUP 4
+#endif
+constexpr int kHbvGroup = RRB_HBV_GROUP;
+
+template <bool WRITEQ, bool STORAGE, bool OBJ>
+__global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
+                                const double* __restrict__ params, int64_t N, HbvOut out, Slab slab,
+                                Objective obj) {
+    const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i = gi < N ? gi : N - 1;  // see hbv_precise_kernel
+    const double* p = params + 11 * i;
+    const double T_t = p[0], DD = p[1], FC = p[2], Beta = p[3], C = p[4], PWP = p[5];
+    const double K_0 = p[6], K_1 = p[7], K_2 = p[8], K_p = p[9], L = p[10];
+    const double inv_FC = 1.0 / FC, inv_PWP = 1.0 / PWP;
+    const double c1 = 1.0 - K_1 - K_p;  // s1 (1 - K_1 - K_p)
+    const double c2 = 1.0 - K_2;        // s2 (1 - K_2)
+    // The table-driven pow is used when soil/FC is within [2^-15, 2^15) and |Beta| < 32 (then
+    // |Beta log2 x| < 512 and x is a positive normal).  The range test is one unsigned compare on the high
+    // word of soil against per-member bounds derived from FC (never true for FC <= 0, NaN, inf, denormal).
+    uint32_t safe_lo = 0u, safe_span = 0u;
+    if (fabs(Beta) < 32.0 && FC > 0x1p-900 && FC < 0x1p900) {
+        safe_lo = (uint32_t)__double2hiint(FC * 0x1p-15) + 1u;
+        safe_span = (uint32_t)__double2hiint(FC * 0x1p15) - safe_lo;
+    }
+    int64_t stride = N;
+#ifndef RRB_X_NOSTRIDE
+    asm volatile("" : "+l"(stride));  // opaque: keep the row stride in registers
+#endif
+
+    double snow = snow0, soil = soil0, s1 = s10, s2 = s20;  // hbvedu_model.py:78-81
+    double acc = 0.0;
+    int64_t t_first = slab.t_begin;
+    int64_t off = i + (slab.t_begin - slab.row0) * N;
+    if (slab.t_begin > 0) {
+        snow = slab.state[0 * N + i];
+        soil = slab.state[1 * N + i];
+        s1 = slab.state[2 * N + i];
+        s2 = slab.state[3 * N + i];
+        if (OBJ) acc = slab.state[4 * N + i];
+    } else {
+        if (WRITEQ) st_stream(out.qsim + off, 0.0);
+        if (STORAGE) {
+            st_stream(out.snow + off, snow);
+            st_stream(out.soil + off, soil);
+            st_stream(out.s1 + off, s1);
+            st_stream(out.s2 + off, s2);
+        }
+        if (OBJ) {
+            const double d = obj.qobs[0];
+            acc = d * d;
+        }
+        off += N;
+        t_first = 1;
+    }
+    double* q_o = WRITEQ ? out.qsim + off : nullptr;
+    double* snow_o = STORAGE ? out.snow + off : nullptr;
+    double* soil_o = STORAGE ? out.soil + off : nullptr;
+    double* s1_o = STORAGE ? out.s1 + off : nullptr;
+    double* s2_o = STORAGE ? out.s2 + off : nullptr;
+
+    extern __shared__ __align__(128) unsigned char rrb_smem[];
+    uint32_t tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<kHbvR, kHbvTT>()));
+    asm volatile("" : "+r"(tb));  // opaque: keep the table base in a register
+
+    stream_forcing_grouped<kHbvR, kHbvTT, kHbvGroup, HbvF>(
+        F, t_first, slab.t_end, [&](auto gc, int64_t t0, const HbvF* f) {
+            constexpr int G = decltype(gc)::value;
+            double liquid[G], pe[G], snow_g[G];
+            bool need[G];
+            // ---- A: snow routine (hbvedu_model.py:87-96), potential evapotranspiration (:102)
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                // both branches are evaluated and selected: no divergent control flow in the group
+                const double m = DD * (f[g].temp - T_t);
+                const double acc_snow = snow + f[g].prec;
+                const double melt_snow = nb_max0(snow - m);
+                const double melt_liq = f[g].prec + nb_min(snow, m);
+                const bool cold = f[g].temp < T_t;
+                snow = cold ? acc_snow : melt_snow;
+                liquid[g] = cold ? 0.0 : melt_liq;
+                snow_g[g] = snow;
+                pe[g] = fma(C, f[g].dT, f[g].PEm);  // FAST packing: dT holds dT * PEm
+            }
+            // ---- prec_eff = liquid * (soil/FC)^Beta (:99) is +0 whenever liquid == 0 and the power is
+            // finite, so a warp evaluates the pow only if one of its members has liquid water
+#pragma unroll
+            for (int g = 0; g < G; ++g) need[g] = __any_sync(0xffffffffu, liquid[g] != 0.0);
+            // ---- B: soil moisture, response routine, discharge
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+#ifdef RRB_X_SAFEX
+                const bool safe = ((uint32_t)__double2hiint(soil * inv_FC) - 0x3EF00000u) < (safe_span ? 0x02000000u : 0u);
+#else
+                const bool safe = ((uint32_t)__double2hiint(soil) - safe_lo) < safe_span;
+#endif
+                const double ea = (soil > PWP) ? pe[g] : pe[g] * (soil * inv_PWP);  // :105-108
+                const double oK = nb_max0(s1 - L) * K_0;
+                const double s2_new = fma(s1, K_p, s2 * c2);                         // :121-123
+                const double s1_base = fma(s1, c1, -oK);
+                const double soil_base = (soil + liquid[g]) - ea;
+                double prec_eff = 0.0;
+#if defined(RRB_EXP_NOPOW)
+                if (false) {
+#elif defined(RRB_EXP_ALWAYSPOW)
+                if (true) {
+#else
+                if (need[g]) {
+#endif
+                    double pw = fast_pow_unchecked_smem(soil * inv_FC, Beta, tb);
+                    if (!safe) pw = hbv_slow_pow(soil, FC, Beta);
+                    prec_eff = liquid[g] * pw;
+                } else if (!safe) {
+                    prec_eff = liquid[g] * hbv_slow_pow(soil, FC, Beta);  // 0 * (inf | nan), as the reference
+                }
+                soil = soil_base - prec_eff;                                         // :111
+                s1 = s1_base + prec_eff;                                             // :114-118
+                s2 = s2_new;
+                const double qv = fma(s2_new, K_2, fma(s1, K_1, oK));                // :125-127
+                if (WRITEQ) {
+                    st_stream(q_o, qv);
+                    q_o += stride;
+                }
+                if (STORAGE) {
+                    st_stream(snow_o, snow_g[g]);
+                    st_stream(soil_o, soil);
+                    st_stream(s1_o, s1);
+                    st_stream(s2_o, s2);
+                    snow_o += stride;
+                    soil_o += stride;
+                    s1_o += stride;
+                    s2_o += stride;
+                }
+                if (OBJ) {
+                    const double d = obj.qobs[t0 + g] - qv;
+                    acc += d * d;
+                }
+            }
+        });
+
+    if (gi < N) {
         if (slab.save_state) {
             slab.state[0 * N + i] = snow;
             slab.state[1 * N + i] = soil;
@@ -151,20 +336,23 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
     const unsigned grid = (unsigned)((N + block - 1) / block);
     const bool fast = cfg.math == RRB_MATH_FAST_;
     const size_t smem = forcing_smem_bytes<kHbvR, kHbvTT>() + (fast ? fastmath_smem_bytes() : 0);
-    const bool st = snow != nullptr, ob = obj.qobs != nullptr;
+    const bool st = snow != nullptr, ob = obj.qobs != nullptr, wq = qsim != nullptr;
     HbvOut out{qsim, snow, soil, s1, s2};
-#define RRB_HBV(M_, S_, O_)                                                                                  \
-    hbv_kernel<M_, S_, O_><<<grid, block, smem, cfg.stream>>>(F, inits4[0], inits4[1], inits4[2], inits4[3], \
-                                                              params, N, out, slab, obj)
-#define RRB_HBV_M(M_)                     \
-    do {                                  \
-        if (st && ob) RRB_HBV(M_, true, true);   \
-        else if (st) RRB_HBV(M_, true, false);   \
-        else if (ob) RRB_HBV(M_, false, true);   \
-        else RRB_HBV(M_, false, false);          \
+#define RRB_HBV(M_, Q_, S_, O_)                                                                                   \
+    M_<Q_, S_, O_><<<grid, block, smem, cfg.stream>>>(F, inits4[0], inits4[1], inits4[2], inits4[3], params, N, out, \
+                                                      slab, obj)
+#define RRB_HBV_M(M_)                                      \
+    do {                                                   \
+        if (wq && st && ob) RRB_HBV(M_, true, true, true);        \
+        else if (wq && st) RRB_HBV(M_, true, true, false);        \
+        else if (wq && ob) RRB_HBV(M_, true, false, true);        \
+        else if (wq) RRB_HBV(M_, true, false, false);             \
+        else if (st && ob) RRB_HBV(M_, false, true, true);        \
+        else if (st) RRB_HBV(M_, false, true, false);             \
+        else RRB_HBV(M_, false, false, true);                     \
     } while (0)
-    if (fast) RRB_HBV_M(RRB_MATH_FAST_);
-    else RRB_HBV_M(RRB_MATH_PRECISE_);
+    if (fast) RRB_HBV_M(hbv_fast_kernel);
+    else RRB_HBV_M(hbv_precise_kernel);
 #undef RRB_HBV_M
 #undef RRB_HBV
     return cudaGetLastError();

@@ -53,7 +53,7 @@ inline int64_t padded_steps(int64_t T, int TT) { return ((T + TT - 1) / TT) * TT
 // ---- forcing packers (device pointers in, packed F[Tpad][R] out) ----
 cudaError_t pack_abc(const double* prec, int64_t T, double* F, cudaStream_t s);
 cudaError_t pack_hbvedu(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
-                        const double* T_m, int64_t T, double* F, cudaStream_t s);
+                        const double* T_m, int64_t T, double* F, int math, cudaStream_t s);
 cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* F, cudaStream_t s);
 // writes F and g_tresh[L] (sequential np.mean semantics, rrmpg/models/cemaneige_model.py:80)
 cudaError_t pack_cemaneige(const double* prec, const double* mean_temp, const double* frac, const double* etp,

@@ -129,6 +129,55 @@ __host__ __device__ __forceinline__ double fast_pow(double x, double y, const Fa
 }
 
 #ifdef __CUDACC__
+// polynomial coefficients in the constant bank: DFMA takes a c[bank][offset] operand directly, so
+// no registers and no per-step immediate moves are spent on them
+static __constant__ double kc_log2_poly[7] = RRB_LOG2_POLY;
+static __constant__ double kc_exp2_poly[6] = RRB_EXP2_POLY;
+
+// Device-side variants reading the tables through a 32-bit shared-window address (see lds_f64x2 in
+// rr_common.cuh for why).  No range checks: the caller guarantees 2^-16 < x < 2^16 and |y| < 32,
+// hence x positive normal and |y log2 x| <= 512.  Out-of-contract operands give garbage, never a fault
+// (table indices are masked).
+__device__ __forceinline__ double fast_pow_unchecked_smem(double x, double y, uint32_t tb_addr) {
+    const double* A = kc_log2_poly;
+    const double* C = kc_exp2_poly;
+    constexpr double kShift = 0x1.8p52 / tables::kExpN;
+    // ---- log2(x)
+    const uint64_t ix = (uint64_t)__double_as_longlong(x);
+    const uint64_t tmp = ix - tables::kLogOff;
+    const uint32_t i = (uint32_t)(tmp >> 45) & (tables::kLogN - 1);
+    const int k = (int)((int64_t)tmp >> 52);
+    const double z = __longlong_as_double((long long)(ix - (tmp & 0xFFF0000000000000ULL)));
+    double invc, log2c;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(log2c) : "r"(tb_addr + i * 16u));
+    const double r = fma(z, invc, -1.0);
+    const double base = (double)k + log2c;
+    const double r2 = r * r;
+    const double a = fma(r, A[1], A[0]);
+    const double b = fma(r, A[3], A[2]);
+    const double c = fma(r, A[5], A[4]);
+    const double r4 = r2 * r2;
+    double t = fma(r2, b, a);
+    t = fma(r4, c, t);
+    const double zz = y * fma(r, t, base);
+    // ---- 2^zz
+    double kd = zz + kShift;
+    const uint64_t ki = (uint64_t)__double_as_longlong(kd);
+    kd -= kShift;
+    const double rr = zz - kd;
+    unsigned long long tj;
+    asm volatile("ld.shared.u64 %0, [%1];"
+                 : "=l"(tj)
+                 : "r"(tb_addr + (uint32_t)(2 * tables::kLogN * 8) + ((uint32_t)ki & (tables::kExpN - 1)) * 8u));
+    const double scale = __longlong_as_double((long long)(tj + (ki << 45)));
+    const double q2 = rr * rr;
+    const double e = fma(rr, C[1], C[0]);
+    double f = fma(rr, C[3], C[2]);
+    f = fma(q2, C[4], f);
+    const double g = fma(q2, f, e);
+    return fma(scale, rr * g, scale);
+}
+
 // v^(-1/4) for v >= 1 finite: fp32 SFU seed refined by one third-order step and one Newton step
 // (result within ~1 ulp).  Used for the (1 + u^4)^(-0.25) terms of rrmpg/models/gr4j_model.py:117,145.
 __device__ __forceinline__ double fast_rsqrt4_ge1(double v) {

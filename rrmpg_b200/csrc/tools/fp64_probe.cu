@@ -1,0 +1,78 @@
+// fp64_probe.cu -- measures the fp64 pipe of the GPU the kernels run on (the second roofline of the
+// recurrence kernels): dependent-issue latency of DFMA/DADD/DMUL, and DFMA throughput as a function of
+// resident warps per SM sub-partition.  Build: nvcc -arch=sm_100a -O3 -o fp64_probe fp64_probe.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int ILP>
+__global__ void dfma_chain(double* out, double a, double b, int iters, long long* cycles) {
+    double x[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) x[k] = a + k + threadIdx.x;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) x[k] = fma(x[k], a, b);
+    }
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) s += x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+__global__ void dadd_chain(double* out, double a, int iters, long long* cycles) {
+    double x = a + threadIdx.x;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) x = x + a;
+    long long t1 = clock64();
+    out[threadIdx.x] = x;
+    if (threadIdx.x == 0) *cycles = t1 - t0;
+}
+
+int main() {
+    double* out; long long* cyc; long long h;
+    cudaMalloc(&out, sizeof(double) * 148 * 1024 * 8);
+    cudaMalloc(&cyc, 8);
+    const int iters = 1 << 16;
+    // latency: 1 warp, 1 chain
+    dfma_chain<1><<<1, 32>>>(out, 1.0000001, 1e-9, iters, cyc);
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("DFMA dependent latency       : %.2f cycles\n", (double)h / iters);
+    dadd_chain<<<1, 32>>>(out, 1e-9, iters, cyc);
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("DADD dependent latency       : %.2f cycles\n", (double)h / iters);
+    dfma_chain<2><<<1, 32>>>(out, 1.0000001, 1e-9, iters, cyc);
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("1 warp, ILP 2: cycles/DFMA   : %.2f\n", (double)h / iters / 2);
+    dfma_chain<8><<<1, 32>>>(out, 1.0000001, 1e-9, iters, cyc);
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("1 warp, ILP 8: cycles/DFMA   : %.2f   (issue interval of one warp)\n", (double)h / iters / 8);
+    // throughput: all SMs, W warps per sub-partition, ILP 4
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    for (int wps : {1, 2, 3, 4, 6, 8, 16}) {
+        const int threads = wps * 4 * 32;  // one CTA per SM
+        dfma_chain<4><<<sms, threads>>>(out, 1.0000001, 1e-9, 1024, cyc);
+        cudaEventRecord(e0);
+        dfma_chain<4><<<sms, threads>>>(out, 1.0000001, 1e-9, iters, cyc);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double dfma = (double)sms * threads * iters * 4;
+        printf("%2d warps/SMSP ILP4: %.2f TDFMA/s (%.1f TFLOP/s), %.3f DFMA/clk/SM @1.965GHz\n", wps, dfma / ms / 1e9,
+               2 * dfma / ms / 1e9, dfma / (ms * 1e-3) / sms / 1.965e9);
+    }
+    for (int wps : {1, 2, 4, 8}) {
+        const int threads = wps * 4 * 32;
+        cudaEventRecord(e0);
+        dfma_chain<1><<<sms, threads>>>(out, 1.0000001, 1e-9, iters, cyc);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double dfma = (double)sms * threads * iters;
+        printf("%2d warps/SMSP ILP1: %.2f TDFMA/s, %.3f DFMA/clk/SM\n", wps, dfma / ms / 1e9,
+               dfma / (ms * 1e-3) / sms / 1.965e9);
+    }
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
