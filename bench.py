@@ -165,7 +165,7 @@ def config_dict(n_gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="fast", choices=["fast", "precise"])
@@ -279,7 +279,7 @@ def main():
         with open(tpath) as fh:
             traffic = json.load(fh).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "rrb::hbv_kernel<FAST, qsim-only>",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "rrb::hbv_fast_kernel<qsim-only>" if args.math == "fast" else "rrb::hbv_precise_kernel<qsim-only>",
                 "kernel_ms": kernel_ms,
                 "note": "algorithmic bytes = 8 B x members x timesteps per launch; duration = CUDA-event time of one "
                         "step (forcing pack kernel + ensemble kernel; the pack kernel is <0.1% of it)"}

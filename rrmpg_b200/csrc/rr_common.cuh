@@ -287,33 +287,30 @@ __device__ __forceinline__ void stream_forcing_grouped(const double* __restrict_
     uint32_t parity = 0;
     for (int64_t k = k_begin; k < k_end; ++k) {
         mbar_wait(&full[stage], parity);
-        const uint32_t base = tiles_addr + (uint32_t)stage * kTileBytes;
         const int64_t t0 = k * TT;
         const int lo = (int)((t_begin > t0) ? (t_begin - t0) : 0);
         const int hi = (int)((t_end < t0 + TT) ? (t_end - t0) : TT);
-        int tt = lo;
-        for (; tt < hi && (tt % G) != 0; ++tt) {  // ragged head
-            FV f1[1] = {FV::load(base + (uint32_t)tt * kRowBytes)};
-            group(ic<1>{}, t0 + tt, f1);
+        uint32_t addr = tiles_addr + (uint32_t)stage * kTileBytes + (uint32_t)lo * kRowBytes;
+        int64_t t = t0 + lo;
+        int left = hi - lo;
+        while (left > 0 && (t % G) != 0) {  // ragged head of a time slab
+            FV f1[1] = {FV::load(addr)};
+            group(ic<1>{}, t, f1);
+            addr += kRowBytes; ++t; --left;
         }
-        if (tt + G <= hi) {
-            FV nxt[G];
+#pragma unroll 1
+        for (int j = left / G; j > 0; --j) {
+            FV f[G];
 #pragma unroll
-            for (int g = 0; g < G; ++g) nxt[g] = FV::load(base + (uint32_t)(tt + g) * kRowBytes);
-            for (; tt + G <= hi; tt += G) {
-                FV cur[G];
-#pragma unroll
-                for (int g = 0; g < G; ++g) cur[g] = nxt[g];
-                // prefetch the next group (clamped inside the tile; a repeated row is never used)
-                const int nt = (tt + 2 * G <= TT) ? tt + G : tt;
-#pragma unroll
-                for (int g = 0; g < G; ++g) nxt[g] = FV::load(base + (uint32_t)(nt + g) * kRowBytes);
-                group(ic<G>{}, t0 + tt, cur);
-            }
+            for (int g = 0; g < G; ++g) f[g] = FV::load(addr + (uint32_t)g * kRowBytes);
+            group(ic<G>{}, t, f);
+            addr += G * kRowBytes;
+            t += G;
         }
-        for (; tt < hi; ++tt) {  // ragged tail
-            FV f1[1] = {FV::load(base + (uint32_t)tt * kRowBytes)};
-            group(ic<1>{}, t0 + tt, f1);
+        for (left %= G; left > 0; --left) {  // ragged tail
+            FV f1[1] = {FV::load(addr)};
+            group(ic<1>{}, t, f1);
+            addr += kRowBytes; ++t;
         }
         __syncthreads();  // every thread is done reading this stage
         if (threadIdx.x == 0 && k + kStages < k_end) {
@@ -328,6 +325,13 @@ __device__ __forceinline__ void stream_forcing_grouped(const double* __restrict_
         }
     }
 }
+
+// keep a loop-invariant value in registers: without this the compiler prefers to recompute cheap
+// expressions (1 - K_2, shared-window bases, ...) inside the time loop, where every fp64 instruction
+// costs two issue slots
+__device__ __forceinline__ void pin(double& v) { asm volatile("" : "+d"(v)); }
+__device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void pin(int64_t& v) { asm volatile("" : "+l"(v)); }
 
 // dynamic shared memory = [forcing ring | mbarriers | (FAST math tables)], rounded to 16 B
 template <int R, int TT>

@@ -174,10 +174,15 @@ __global__ void hbv_precise_kernel(const double* __restrict__ F, double snow0, d
 // chain), then the B chains, each either with or without the pow.
 // ------------------------------------------------------------------------------------------------
 #ifndef RRB_HBV_GROUP
-#define RRB_HBV_GROUP 4
+#define RRB_HBV_GROUP 2
 #endif
 constexpr int kHbvGroup = RRB_HBV_GROUP;
 
+// Cost model (measured, profiles/r01_*): with one thread per member the 65 536-member workload leaves 3.5
+// warps per SM sub-partition and the kernel is ISSUE bound -- every fp64 instruction holds the issue port
+// for 2 cycles (16 fp64 lanes per sub-partition), every other instruction for 1.  The body below is written
+// to minimise (2 x fp64 + other) instructions per member-timestep: ~22 fp64 + ~25 other without the pow,
+// ~27 fp64 + ~15 other more with it.
 template <bool WRITEQ, bool STORAGE, bool OBJ>
 __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                                 const double* __restrict__ params, int64_t N, HbvOut out, Slab slab,
@@ -187,9 +192,9 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
     const double* p = params + 11 * i;
     const double T_t = p[0], DD = p[1], FC = p[2], Beta = p[3], C = p[4], PWP = p[5];
     const double K_0 = p[6], K_1 = p[7], K_2 = p[8], K_p = p[9], L = p[10];
-    const double inv_FC = 1.0 / FC, inv_PWP = 1.0 / PWP;
-    const double c1 = 1.0 - K_1 - K_p;  // s1 (1 - K_1 - K_p)
-    const double c2 = 1.0 - K_2;        // s2 (1 - K_2)
+    double inv_FC = 1.0 / FC, inv_PWP = 1.0 / PWP;
+    double c1 = 1.0 - K_1 - K_p;  // s1 (1 - K_1 - K_p)
+    double c2 = 1.0 - K_2;        // s2 (1 - K_2)
     // The table-driven pow is used when soil/FC is within [2^-15, 2^15) and |Beta| < 32 (then
     // |Beta log2 x| < 512 and x is a positive normal).  The range test is one unsigned compare on the high
     // word of soil against per-member bounds derived from FC (never true for FC <= 0, NaN, inf, denormal).
@@ -199,9 +204,7 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
         safe_span = (uint32_t)__double2hiint(FC * 0x1p15) - safe_lo;
     }
     int64_t stride = N;
-#ifndef RRB_X_NOSTRIDE
-    asm volatile("" : "+l"(stride));  // opaque: keep the row stride in registers
-#endif
+    pin(inv_FC); pin(inv_PWP); pin(c1); pin(c2); pin(safe_lo); pin(safe_span); pin(stride);
 
     double snow = snow0, soil = soil0, s1 = s10, s2 = s20;  // hbvedu_model.py:78-81
     double acc = 0.0;
@@ -236,22 +239,26 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
 
     extern __shared__ __align__(128) unsigned char rrb_smem[];
     uint32_t tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<kHbvR, kHbvTT>()));
-    asm volatile("" : "+r"(tb));  // opaque: keep the table base in a register
+    pin(tb);
+    __syncthreads();  // the staged tables are visible
+    const PowRegs pr = load_pow_regs(tb);
 
     stream_forcing_grouped<kHbvR, kHbvTT, kHbvGroup, HbvF>(
         F, t_first, slab.t_end, [&](auto gc, int64_t t0, const HbvF* f) {
             constexpr int G = decltype(gc)::value;
             double liquid[G], pe[G], snow_g[G];
             bool need[G];
-            // ---- A: snow routine (hbvedu_model.py:87-96), potential evapotranspiration (:102)
+            // ---- A: snow routine (hbvedu_model.py:87-96), potential evapotranspiration (:102).
+            // Both branches are evaluated and selected.  max(0, snow - m) and min(snow, m) share one
+            // predicate: snow - m > 0 <=> m < snow for every operand pair (NaN and inf included).
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                // both branches are evaluated and selected: no divergent control flow in the group
                 const double m = DD * (f[g].temp - T_t);
-                const double acc_snow = snow + f[g].prec;
-                const double melt_snow = nb_max0(snow - m);
-                const double melt_liq = f[g].prec + nb_min(snow, m);
+                const bool melt_all = !(m < snow);
+                const double melt_snow = melt_all ? 0.0 : snow - m;
+                const double melt_liq = f[g].prec + (melt_all ? snow : m);
                 const bool cold = f[g].temp < T_t;
+                const double acc_snow = snow + f[g].prec;
                 snow = cold ? acc_snow : melt_snow;
                 liquid[g] = cold ? 0.0 : melt_liq;
                 snow_g[g] = snow;
@@ -264,17 +271,12 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
             // ---- B: soil moisture, response routine, discharge
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-#ifdef RRB_X_SAFEX
-                const bool safe = ((uint32_t)__double2hiint(soil * inv_FC) - 0x3EF00000u) < (safe_span ? 0x02000000u : 0u);
-#else
                 const bool safe = ((uint32_t)__double2hiint(soil) - safe_lo) < safe_span;
-#endif
                 const double ea = (soil > PWP) ? pe[g] : pe[g] * (soil * inv_PWP);  // :105-108
                 const double oK = nb_max0(s1 - L) * K_0;
                 const double s2_new = fma(s1, K_p, s2 * c2);                         // :121-123
-                const double s1_base = fma(s1, c1, -oK);
-                const double soil_base = (soil + liquid[g]) - ea;
-                double prec_eff = 0.0;
+                double s1_new = fma(s1, c1, -oK);                                    // :114-118 without prec_eff
+                double soil_new = (soil + liquid[g]) - ea;                           // :111 without prec_eff
 #if defined(RRB_EXP_NOPOW)
                 if (false) {
 #elif defined(RRB_EXP_ALWAYSPOW)
@@ -282,16 +284,20 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
 #else
                 if (need[g]) {
 #endif
-                    double pw = fast_pow_unchecked_smem(soil * inv_FC, Beta, tb);
+                    double pw = fast_pow_unchecked_smem(soil * inv_FC, Beta, tb, pr);
                     if (!safe) pw = hbv_slow_pow(soil, FC, Beta);
-                    prec_eff = liquid[g] * pw;
+                    const double prec_eff = liquid[g] * pw;
+                    soil_new -= prec_eff;
+                    s1_new += prec_eff;
                 } else if (!safe) {
-                    prec_eff = liquid[g] * hbv_slow_pow(soil, FC, Beta);  // 0 * (inf | nan), as the reference
+                    const double prec_eff = liquid[g] * hbv_slow_pow(soil, FC, Beta);  // 0 * (inf | nan)
+                    soil_new -= prec_eff;
+                    s1_new += prec_eff;
                 }
-                soil = soil_base - prec_eff;                                         // :111
-                s1 = s1_base + prec_eff;                                             // :114-118
+                soil = soil_new;
+                s1 = s1_new;
                 s2 = s2_new;
-                const double qv = fma(s2_new, K_2, fma(s1, K_1, oK));                // :125-127
+                const double qv = fma(s2_new, K_2, fma(s1_new, K_1, oK));            // :125-127
                 if (WRITEQ) {
                     st_stream(q_o, qv);
                     q_o += stride;

@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <stddef.h>
 
 #include "rr_math_tables.h"
 
@@ -30,12 +31,14 @@ struct FastTables {
     double log2tab[2 * tables::kLogN];           // {invc, log2c}
     unsigned long long exp2tab[tables::kExpN];   // bits(2^(j/128)) - (j << 45)
     double exp2m1tab[tables::kExpN];             // 2^(j/128) - 1
+    double log2poly[8];                          // log2(1+r)/r coefficients (7 used)
+    double exp2poly[8];                          // (2^r - 1)/r coefficients (6 used)
 };
 
 #ifdef __CUDACC__
-static __device__ const FastTables d_fast_tables = {RRB_LOG2_TABLE, RRB_EXP2_TABLE, RRB_EXP2M1_TABLE};
+static __device__ const FastTables d_fast_tables = {RRB_LOG2_TABLE, RRB_EXP2_TABLE, RRB_EXP2M1_TABLE, RRB_LOG2_POLY, RRB_EXP2_POLY};
 #endif
-static const FastTables h_fast_tables = {RRB_LOG2_TABLE, RRB_EXP2_TABLE, RRB_EXP2M1_TABLE};
+static const FastTables h_fast_tables = {RRB_LOG2_TABLE, RRB_EXP2_TABLE, RRB_EXP2M1_TABLE, RRB_LOG2_POLY, RRB_EXP2_POLY};
 
 __host__ __device__ __forceinline__ uint64_t f64_bits(double x) {
 #ifdef __CUDA_ARCH__
@@ -134,48 +137,79 @@ __host__ __device__ __forceinline__ double fast_pow(double x, double y, const Fa
 static __constant__ double kc_log2_poly[7] = RRB_LOG2_POLY;
 static __constant__ double kc_exp2_poly[6] = RRB_EXP2_POLY;
 
+// polynomial coefficients as a kernel parameter: they then live in the parameter constant bank and
+// DFMA reads them as c[0x0][offset] operands -- no registers, no LDC / MOV instructions in the loop
+struct PowCoef {
+    double A[7];  // log2(1+r) = r (A0 + A1 r + ... )
+    double C[6];  // 2^r - 1   = r (C0 + C1 r + ... )
+};
+inline PowCoef make_pow_coef() {
+    PowCoef c = {RRB_LOG2_POLY, RRB_EXP2_POLY};
+    return c;
+}
+
 // Device-side variants reading the tables through a 32-bit shared-window address (see lds_f64x2 in
 // rr_common.cuh for why).  No range checks: the caller guarantees 2^-16 < x < 2^16 and |y| < 32,
 // hence x positive normal and |y log2 x| <= 512.  Out-of-contract operands give garbage, never a fault
 // (table indices are masked).
-__device__ __forceinline__ double fast_pow_unchecked_smem(double x, double y, uint32_t tb_addr) {
-    const double* A = kc_log2_poly;
-    const double* C = kc_exp2_poly;
+// Coefficients held in registers for the whole kernel (load once from the parameter bank, then pin()):
+// an FMA can take only one constant-bank operand, so polynomial steps of the form fma(r, c1, c0) would
+// otherwise need a load per step.
+struct PowRegs {
+    double a0, a1, a2, a3, a4, a5;  // log2(1+r)/r, degree 5
+    double c0, c1, c2, c3, c4;      // (2^r - 1)/r, degree 4
+};
+
+__device__ __forceinline__ double fast_pow_unchecked_smem(double x, double y, uint32_t tb_addr, const PowRegs& pc) {
     constexpr double kShift = 0x1.8p52 / tables::kExpN;
-    // ---- log2(x)
-    const uint64_t ix = (uint64_t)__double_as_longlong(x);
-    const uint64_t tmp = ix - tables::kLogOff;
-    const uint32_t i = (uint32_t)(tmp >> 45) & (tables::kLogN - 1);
-    const int k = (int)((int64_t)tmp >> 52);
-    const double z = __longlong_as_double((long long)(ix - (tmp & 0xFFF0000000000000ULL)));
+    // ---- log2(x); all index / exponent work on the high word (the low word passes through unchanged)
+    const uint32_t hx = (uint32_t)__double2hiint(x);
+    const uint32_t ht = hx - (uint32_t)(tables::kLogOff >> 32);
+    const int k = (int)ht >> 20;
+    const double z = __hiloint2double((int)(hx - (ht & 0xFFF00000u)), __double2loint(x));
     double invc, log2c;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(log2c) : "r"(tb_addr + i * 16u));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(log2c) : "r"(tb_addr + ((ht >> 9) & 0x7F0u)));
     const double r = fma(z, invc, -1.0);
     const double base = (double)k + log2c;
     const double r2 = r * r;
-    const double a = fma(r, A[1], A[0]);
-    const double b = fma(r, A[3], A[2]);
-    const double c = fma(r, A[5], A[4]);
+    const double a = fma(r, pc.a1, pc.a0);
+    const double b = fma(r, pc.a3, pc.a2);
+    const double c = fma(r, pc.a5, pc.a4);
     const double r4 = r2 * r2;
     double t = fma(r2, b, a);
     t = fma(r4, c, t);
     const double zz = y * fma(r, t, base);
     // ---- 2^zz
     double kd = zz + kShift;
-    const uint64_t ki = (uint64_t)__double_as_longlong(kd);
+    const uint32_t ki = (uint32_t)__double2loint(kd);  // round(128 zz), two's complement
     kd -= kShift;
     const double rr = zz - kd;
-    unsigned long long tj;
-    asm volatile("ld.shared.u64 %0, [%1];"
-                 : "=l"(tj)
-                 : "r"(tb_addr + (uint32_t)(2 * tables::kLogN * 8) + ((uint32_t)ki & (tables::kExpN - 1)) * 8u));
-    const double scale = __longlong_as_double((long long)(tj + (ki << 45)));
+    uint32_t tlo, thi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                 : "=r"(tlo), "=r"(thi)
+                 : "r"(tb_addr + (uint32_t)(2 * tables::kLogN * 8) + (ki & (tables::kExpN - 1)) * 8u));
+    const double scale = __hiloint2double((int)(thi + (ki << 13)), (int)tlo);  // bits + (ki << 45)
     const double q2 = rr * rr;
-    const double e = fma(rr, C[1], C[0]);
-    double f = fma(rr, C[3], C[2]);
-    f = fma(q2, C[4], f);
+    const double e = fma(rr, pc.c1, pc.c0);
+    double f = fma(rr, pc.c3, pc.c2);
+    f = fma(q2, pc.c4, f);
     const double g = fma(q2, f, e);
     return fma(scale, rr * g, scale);
+}
+
+// coefficients come from the shared-memory copy of the tables through volatile loads: values the
+// assembler cannot re-materialise, so they stay in registers for the whole time loop
+__device__ __forceinline__ double lds_f64_at(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ PowRegs load_pow_regs(uint32_t tb_addr) {
+    const uint32_t a = tb_addr + (uint32_t)offsetof(FastTables, log2poly);
+    const uint32_t c = tb_addr + (uint32_t)offsetof(FastTables, exp2poly);
+    return PowRegs{lds_f64_at(a), lds_f64_at(a + 8), lds_f64_at(a + 16), lds_f64_at(a + 24), lds_f64_at(a + 32),
+                   lds_f64_at(a + 40), lds_f64_at(c), lds_f64_at(c + 8), lds_f64_at(c + 16), lds_f64_at(c + 24),
+                   lds_f64_at(c + 32)};
 }
 
 // v^(-1/4) for v >= 1 finite: fp32 SFU seed refined by one third-order step and one Newton step
