@@ -77,25 +77,50 @@ struct CemaOut {
     double *q, *G, *eTG, *s_store, *r_store;
 };
 
-template <int LC, class Gr4j, bool FAST>
+template <int LC>
+struct CemaF {  // forcing of one timestep: { snow[LC] | rain[LC] | mean_temp[LC] | etp | pad }
+    static constexpr int R = CemaGeom<LC>::R;
+    double v[R];
+    static __device__ __forceinline__ CemaF load(uint32_t addr) {
+        CemaF f;
+#pragma unroll
+        for (int k = 0; k < R; k += 2) {
+            const double2 a = lds_f64x2(addr + 8u * k);
+            f.v[k] = a.x;
+            f.v[k + 1] = a.y;
+        }
+        return f;
+    }
+};
+
+// PLAIN = discharge only (no storages, no fused objective): the output flags are compile-time constants
+// EXACT = the run has exactly LC layers (L == LC): the per-layer bound checks fold away
+template <int LC, class Gr4j, bool FAST, bool PLAIN, bool EXACT>
 __global__ void cema_kernel(const double* __restrict__ F, const double* __restrict__ g_tresh, int L, double g0,
                             double e0, double s_init, double r_init, const double* __restrict__ params,
                             int64_t pstride, int64_t N, CemaOut out, Slab slab, Objective obj) {
     constexpr bool COUPLED = Gr4j::kStateSlots > 0;
     constexpr int R = CemaGeom<LC>::R, TT = CemaGeom<LC>::TT;
-    const bool STORAGE = out.G != nullptr, OBJ = obj.qobs != nullptr;  // CTA-uniform
+    const bool WRITEQ = PLAIN || out.q != nullptr, STORAGE = !PLAIN && out.G != nullptr,
+               OBJ = !PLAIN && obj.qobs != nullptr;  // CTA-uniform
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const bool active = gi < N;
-    const int64_t i = active ? gi : N - 1;
+    // threads past the end of the ensemble recompute member N-1 and store the same values to the same
+    // addresses: no predicate lives in the time loop
+    const int64_t i = gi < N ? gi : N - 1;
     // record = (CTG, Kf[, x1, x2, x3, x4]) -- rrmpg/models/cemaneige.py:64-65, cemaneigegr4j.py:67-72
     const double CTG = params[pstride * i + 0], Kf = params[pstride * i + 1];
-    const double omCTG = 1 - CTG;  // loop invariant of cemaneige_model.py:94
-    double G[LC], eTG[LC], gt[LC];
+    double omCTG = 1 - CTG;  // loop invariant of cemaneige_model.py:94
+    pin(omCTG);
+    if (EXACT) L = LC;
+    double G[LC], eTG[LC], gt[LC], inv_gt[LC];
+    uint32_t gt_span[LC];
 #pragma unroll
     for (int l = 0; l < LC; ++l) {
         G[l] = 0.0;
         eTG[l] = 0.0;
         gt[l] = (l < L) ? g_tresh[l] : 0.0;
+        inv_gt[l] = 1.0 / gt[l];
+        gt_span[l] = div_invariant_span(gt[l]);
     }
     Gr4j gr;
     if constexpr (COUPLED) gr.init(params + pstride * i + 2, s_init, r_init);
@@ -110,62 +135,95 @@ __global__ void cema_kernel(const double* __restrict__ F, const double* __restri
         if constexpr (COUPLED) gr.load(slab.state + (int64_t)2 * LC * N, N, i);
         if (OBJ) acc = slab.state[(int64_t)kSlots * N + i];
     }
-    const int64_t off = i - slab.row0 * N;
-    const int64_t offL = i - slab.row0 * L * N;  // [rows, L, N] storages
-    double* q_o = out.q ? out.q + off : nullptr;
+    int64_t stride = N, strideL = (int64_t)L * N;
+    pin(stride); pin(strideL);
+    const int64_t off = i + (slab.t_begin - slab.row0) * N;
+    double* q_o = WRITEQ ? out.q + off : nullptr;
+    double* s_o = (COUPLED && STORAGE) ? out.s_store + off : nullptr;
+    double* r_o = (COUPLED && STORAGE) ? out.r_store + off : nullptr;
+    double* G_o = STORAGE ? out.G + i + (slab.t_begin - slab.row0) * L * N : nullptr;  // [rows, L, N]
+    double* E_o = STORAGE ? out.eTG + i + (slab.t_begin - slab.row0) * L * N : nullptr;
     const double layers = (double)L;
+    double inv_layers = 1.0 / layers;
+    pin(inv_layers);
 
     extern __shared__ __align__(128) unsigned char rrb_smem[];
-    const FastTables* tb = nullptr;
-    if (COUPLED && FAST) tb = fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<R, TT>());
+    uint32_t tb = 0;
+    if (COUPLED && FAST) {
+        tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<R, TT>()));
+        pin(tb);
+    }
 
-    stream_forcing<R, TT>(F, slab.t_begin, slab.t_end, [&](int64_t t, const double* f) {
+    // one timestep; FIRST = the very first step of the series, where the stores take their initial values
+    // instead of being updated (cemaneige_model.py:85-92)
+    auto step = [&](auto first_c, int64_t t, const double* f) {
+        constexpr bool FIRST = decltype(first_c)::value != 0;
         double lw_sum = 0.0;
 #pragma unroll
         for (int l = 0; l < LC; ++l) {
-            if (l < L) {
+            if (EXACT || l < L) {
                 const double snow = f[l], rain = f[LC + l], Tm = f[2 * LC + l];
-                double g = (t == 0) ? g0 : G[l] + snow;                      // :85-88
-                double e = (t == 0) ? e0 : CTG * eTG[l] + omCTG * Tm;        // :91-94
-                if (e > 0) e = 0.0;                                          // :95-96
-                double pot = 0.0;
-                if (e == 0 && Tm > 0) {                                      // :99
-                    pot = Kf * Tm;                                           // :100
-                    if (pot > g) pot = g;                                    // :103-104
-                }
-                double ratio = 1.0;                                          // :112
-                if (g < gt[l] && !(pot == 0.0 && g >= 0.0)) ratio = g / gt[l];  // :109-110
-                const double melt = (0.9 * ratio + 0.1) * pot;               // :115
-                g = g - melt;                                                // :118
-                lw_sum += rain + melt;                                       // :121, :125
+                double g = FIRST ? g0 : G[l] + snow;                      // :85-88
+                double e = FIRST ? e0 : CTG * eTG[l] + omCTG * Tm;        // :91-94
+                e = (e > 0) ? 0.0 : e;                                    // :95-96
+                // potential melt (:99-106), branch-free
+                const double kt = Kf * Tm;
+                const double capped = (kt > g) ? g : kt;
+                const double pot = (e == 0 && Tm > 0) ? capped : 0.0;
+                // snow-covered-area ratio (:109-112).  The division is only evaluated where it can change the
+                // result: with pot == 0 and a non-negative pack the product (0.9 ratio + 0.1) * pot is +0 for
+                // every ratio in [0, 1] (the sign-bit test over-approximates "G < 0", which is harmless).
+                double ratio = 1.0;
+                if (g < gt[l] && (pot != 0.0 || __double2hiint(g) < 0))
+                    ratio = div_by_invariant(g, gt[l], inv_gt[l], gt_span[l]);
+                const double melt = (0.9 * ratio + 0.1) * pot;            // :115
+                g = g - melt;                                             // :118
+                lw_sum += rain + melt;                                    // :121, :125
                 G[l] = g;
                 eTG[l] = e;
-                if (STORAGE && active) {
-                    const int64_t o = offL + (t * L + l) * N;
-                    st_stream(out.G + o, g);
-                    st_stream(out.eTG + o, e);
+                if (STORAGE) {
+                    st_stream(G_o + (int64_t)l * stride, g);
+                    st_stream(E_o + (int64_t)l * stride, e);
                 }
             }
         }
-        const double liquid = (L == 1) ? lw_sum : lw_sum / layers;  // np.mean over layers, :124-125 (x/1 == x)
+        // np.mean over the layers (:124-125); x / 1 == x
+        const double liquid = (L == 1) ? lw_sum : div_by_invariant(lw_sum, layers, inv_layers, kDivSpanOk);
         double qv = liquid;
         if constexpr (COUPLED) qv = gr.step(liquid, f[3 * LC], tb);  // cemaneigegr4j_model.py:62
-        if (active) {
-            if (q_o) st_stream(q_o + t * N, qv);
+        if (WRITEQ) {
+            st_stream(q_o, qv);
+            q_o += stride;
+        }
+        if (STORAGE) {
+            G_o += strideL;
+            E_o += strideL;
             if constexpr (COUPLED) {
-                if (STORAGE) {
-                    st_stream(out.s_store + off + t * N, gr.S);
-                    st_stream(out.r_store + off + t * N, gr.R);
-                }
+                st_stream(s_o, gr.S);
+                st_stream(r_o, gr.R);
+                s_o += stride;
+                r_o += stride;
             }
         }
         if (OBJ) {
             const double d = obj.qobs[t] - qv;
             acc += d * d;
         }
+    };
+
+    int64_t t_first = slab.t_begin;
+    if (slab.t_begin == 0 && slab.t_end > 0) {  // t = 0 peeled: its forcing row comes straight from global memory
+        double f0[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) f0[k] = F[k];
+        step(ic<1>{}, 0, f0);
+        t_first = 1;
+    }
+    stream_forcing_grouped<R, TT, 1, CemaF<LC>>(F, t_first, slab.t_end, [&](auto, int64_t t, const CemaF<LC>* fp) {
+        step(ic<0>{}, t, fp[0].v);
     });
 
-    if (active) {
+    if (gi < N) {
         if (slab.save_state) {
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
@@ -206,8 +264,14 @@ static cudaError_t launch_variant(const double* F, const double* g_tresh, int L,
     const int block = cfg.block > 0 ? cfg.block : pick_block(N, cfg.sm_count, 128);
     const unsigned grid = (unsigned)((N + block - 1) / block);
     const size_t smem = forcing_smem_bytes<R, TT>() + ((FAST && Gr4j::kStateSlots > 0) ? fastmath_smem_bytes() : 0);
-    cema_kernel<LC, Gr4j, FAST><<<grid, block, smem, cfg.stream>>>(F, g_tresh, L, g0, e0, s_init, r_init, params,
-                                                                   pstride, N, out, slab, obj);
+    const bool plain = out.q && !out.G && !obj.qobs;
+#define RRB_CEMA(P_, E_)                                                                                             \
+    cema_kernel<LC, Gr4j, FAST, P_, E_><<<grid, block, smem, cfg.stream>>>(F, g_tresh, L, g0, e0, s_init, r_init, params, \
+                                                                           pstride, N, out, slab, obj)
+    if (plain && L == LC) RRB_CEMA(true, true);
+    else if (L == LC) RRB_CEMA(false, true);
+    else RRB_CEMA(false, false);
+#undef RRB_CEMA
     return cudaGetLastError();
 }
 

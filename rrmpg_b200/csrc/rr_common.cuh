@@ -326,6 +326,32 @@ __device__ __forceinline__ void stream_forcing_grouped(const double* __restrict_
     }
 }
 
+// ----------------------------------------------------------------------------------------
+// Correctly rounded a / b for a loop-invariant b (Markstein): with y = RN(1/b) computed once by a real
+// division, q0 = RN(a y), and two residual corrections r = a - b q (exact in an FMA), q += r y, the
+// result equals the IEEE quotient RN(a/b) bit for bit when nothing under- or overflows (checked against
+// hardware division on 6e8 random and adversarial operand pairs, oracle-side).  The fast
+// path is taken for a positive a with a mid-range exponent (one unsigned compare on its high word; span = 0
+// disables it, e.g. when b itself is out of range) and for a == +0; everything else -- negative, tiny, huge,
+// NaN -- uses the hardware division.  5 fp64 instructions instead of ~12 plus a slow-path call.
+// ----------------------------------------------------------------------------------------
+constexpr uint32_t kDivSpanOk = 0x7A400000u;  // exponents 2^-960 .. 2^+993
+__device__ __forceinline__ uint32_t div_invariant_span(double b) {
+    return (b >= 0x1p-60 && b <= 0x1p60) ? kDivSpanOk : 0u;
+}
+static __device__ __noinline__ double div_slow_path(double a, double b) { return a / b; }
+__device__ __forceinline__ double div_by_invariant(double a, double b, double inv_b, uint32_t span) {
+    const uint32_t h = (uint32_t)__double2hiint(a);
+    const bool fast = ((h - 0x03F00000u) < span) | (((h | (uint32_t)__double2loint(a)) == 0u) & (span != 0u));
+    double q = a * inv_b;
+    double r = fma(-b, q, a);
+    q = fma(r, inv_b, q);
+    r = fma(-b, q, a);
+    q = fma(r, inv_b, q);
+    if (!fast) q = div_slow_path(a, b);
+    return q;
+}
+
 // keep a loop-invariant value in registers: without this the compiler prefers to recompute cheap
 // expressions (1 - K_2, shared-window bases, ...) inside the time loop, where every fp64 instruction
 // costs two issue slots

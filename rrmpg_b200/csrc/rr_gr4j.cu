@@ -28,15 +28,28 @@ cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* 
     return cudaGetLastError();
 }
 
-template <class Member, bool FAST>
+struct Gr4jF {  // forcing of one timestep
+    double prec, etp;
+    static __device__ __forceinline__ Gr4jF load(uint32_t addr) {
+        const double2 a = lds_f64x2(addr);
+        return Gr4jF{a.x, a.y};
+    }
+};
+
+constexpr int kGr4jGroup = 2;
+
+// PLAIN = discharge only (no storages, no fused objective): the output flags are compile-time constants
+template <class Member, bool FAST, bool PLAIN>
 __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double r_init,
                             const double* __restrict__ params, int64_t N, double* __restrict__ qsim,
                             double* __restrict__ s_store, double* __restrict__ r_store, Slab slab,
                             Objective obj) {
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const bool active = gi < N;
-    const int64_t i = active ? gi : N - 1;
-    const bool STORAGE = s_store != nullptr, OBJ = obj.qobs != nullptr;  // CTA-uniform
+    // threads past the end of the ensemble recompute member N-1 and store the same values to the same
+    // addresses: no predicate lives in the time loop
+    const int64_t i = gi < N ? gi : N - 1;
+    const bool WRITEQ = PLAIN || qsim != nullptr, STORAGE = !PLAIN && s_store != nullptr,
+               OBJ = !PLAIN && obj.qobs != nullptr;  // CTA-uniform
     Member m;
     m.init(params + 4 * i, s_init, r_init);  // record = (x1, x2, x3, x4), rrmpg/models/gr4j.py:57-60
     double acc = 0.0;
@@ -44,30 +57,44 @@ __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double 
         m.load(slab.state, N, i);
         if (OBJ) acc = slab.state[(int64_t)Member::kStateSlots * N + i];
     }
-    const int64_t off = i - slab.row0 * N;
-    double* q_o = qsim ? qsim + off : nullptr;
+    int64_t stride = N;
+    pin(stride);
+    const int64_t off = i + (slab.t_begin - slab.row0) * N;
+    double* q_o = WRITEQ ? qsim + off : nullptr;
+    double* s_o = STORAGE ? s_store + off : nullptr;
+    double* r_o = STORAGE ? r_store + off : nullptr;
 
     extern __shared__ __align__(128) unsigned char rrb_smem[];
-    const FastTables* tb = nullptr;
-    if (FAST) tb = fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<kGr4jR, kGr4jTT>());
+    uint32_t tb = 0;
+    if (FAST) {
+        tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<kGr4jR, kGr4jTT>()));
+        pin(tb);
+    }
 
-    stream_forcing<kGr4jR, kGr4jTT>(F, slab.t_begin, slab.t_end, [&](int64_t t, const double* f) {
-        const double2 pe = *reinterpret_cast<const double2*>(f);
-        const double qv = m.step(pe.x, pe.y, tb);
-        if (active) {
-            if (q_o) st_stream(q_o + t * N, qv);
-            if (STORAGE) {
-                st_stream(s_store + off + t * N, m.S);
-                st_stream(r_store + off + t * N, m.R);
+    stream_forcing_grouped<kGr4jR, kGr4jTT, kGr4jGroup, Gr4jF>(
+        F, slab.t_begin, slab.t_end, [&](auto gc, int64_t t0, const Gr4jF* f) {
+            constexpr int G = decltype(gc)::value;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const double qv = m.step(f[g].prec, f[g].etp, tb);
+                if (WRITEQ) {
+                    st_stream(q_o, qv);
+                    q_o += stride;
+                }
+                if (STORAGE) {
+                    st_stream(s_o, m.S);
+                    st_stream(r_o, m.R);
+                    s_o += stride;
+                    r_o += stride;
+                }
+                if (OBJ) {
+                    const double d = obj.qobs[t0 + g] - qv;
+                    acc += d * d;
+                }
             }
-        }
-        if (OBJ) {
-            const double d = obj.qobs[t] - qv;
-            acc += d * d;
-        }
-    });
+        });
 
-    if (active) {
+    if (gi < N) {
         if (slab.save_state) {
             m.save(slab.state, N, i);
             if (OBJ) slab.state[(int64_t)Member::kStateSlots * N + i] = acc;
@@ -101,8 +128,12 @@ static cudaError_t launch_variant(const double* F, double s_init, double r_init,
     const int block = cfg.block > 0 ? cfg.block : pick_block(N, cfg.sm_count, 128);
     const unsigned grid = (unsigned)((N + block - 1) / block);
     const size_t smem = forcing_smem_bytes<kGr4jR, kGr4jTT>() + (FAST ? fastmath_smem_bytes() : 0);
-    gr4j_kernel<Member, FAST><<<grid, block, smem, cfg.stream>>>(F, s_init, r_init, params, N, qsim, s_store, r_store,
-                                                                 slab, obj);
+    if (qsim && !s_store && !obj.qobs)
+        gr4j_kernel<Member, FAST, true><<<grid, block, smem, cfg.stream>>>(F, s_init, r_init, params, N, qsim, s_store,
+                                                                           r_store, slab, obj);
+    else
+        gr4j_kernel<Member, FAST, false><<<grid, block, smem, cfg.stream>>>(F, s_init, r_init, params, N, qsim, s_store,
+                                                                            r_store, slab, obj);
     return cudaGetLastError();
 }
 

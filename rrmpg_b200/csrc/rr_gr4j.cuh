@@ -13,12 +13,12 @@
 
 namespace rrb {
 
-__device__ __forceinline__ double gr4j_s_curve1(int t, double x4) {  // gr4j_model.py:159-173
+static __device__ __noinline__ double gr4j_s_curve1(int t, double x4) {  // gr4j_model.py:159-173
     if (t <= 0) return 0.0;
     else if ((double)t < x4) return pow((double)t / x4, 2.5);
     else return 1.0;
 }
-__device__ __forceinline__ double gr4j_s_curve2(int t, double x4) {  // gr4j_model.py:176-192
+static __device__ __noinline__ double gr4j_s_curve2(int t, double x4) {  // gr4j_model.py:176-192
     if (t <= 0) return 0.0;
     else if ((double)t <= x4) return 0.5 * pow((double)t / x4, 2.5);
     else if ((double)t < 2 * x4) return 1 - 0.5 * pow(2 - (double)t / x4, 2.5);
@@ -28,7 +28,7 @@ __device__ __forceinline__ double gr4j_s_curve2(int t, double x4) {  // gr4j_mod
 template <int C1, int C2, int MATH>
 struct Gr4jMember {
     double x1, x2, x3;
-    double inv_x1, inv_x3, k_tanh;  // FAST: 1/x1, 1/x3, 2 log2(e) / x1
+    double inv_x1, inv_x3, k_tanh, k49;  // FAST: 1/x1, 1/x3, 2 log2(e) / x1, (4/9) / x1
     int n1, n2;
     double o1[C1], o2[C2];  // unit hydrograph ordinates
     double u1[C1], u2[C2];  // routed water still in the unit hydrographs
@@ -41,6 +41,8 @@ struct Gr4jMember {
         const double x4 = p[3];
         inv_x1 = 1.0 / x1; inv_x3 = 1.0 / x3;
         k_tanh = 2.8853900817779268 / x1;  // 2 / ln 2
+        k49 = (4.0 / 9.0) / x1;
+        if (MATH == RRB_MATH_FAST_) { pin(inv_x1); pin(inv_x3); pin(k_tanh); pin(k49); }
         S = s_init * x1;  // :64
         R = r_init * x3;  // :65
         n1 = (int)ceil(x4);          // :68
@@ -77,37 +79,22 @@ struct Gr4jMember {
     }
 
     // one timestep: P = precipitation (or Cemaneige liquid outflow), E = potential evapotranspiration
-    __device__ __forceinline__ double step(double P, double E, const FastTables* tb) {
+    __device__ __forceinline__ double step(double P, double E, uint32_t tb) {
+        if (MATH == RRB_MATH_FAST_) return step_fast(P, E, tb);
         const bool wet = P >= E;                   // :89
         const double arg = wet ? P - E : E - P;    // p_n (:90) or pe_n (:101)
         const double p_n = wet ? arg : 0.0;
-        double frac, perc, gw, q_r;
-        if (MATH == RRB_MATH_FAST_) {
-            const double sr = S * inv_x1;
-            // tanh(a) = m / (m + 2), m = expm1(2a): both branch formulas collapse to num*m / (2 + c*m)
-            const double m = fast_exp2m1_nonneg(arg * k_tanh, tb);
-            const double num = wet ? x1 * (1 - sr * sr) : S * (2 - sr);
-            const double c = wet ? 1 + sr : 2 - sr;
-            frac = (num * m) / fma(c, m, 2.0);
-        } else {
-            const double sr = S / x1;
-            const double th = tanh(arg / x1);
-            const double num = wet ? (x1 * (1 - sr * sr)) * th : (S * (2 - sr)) * th;  // :95 / :107
-            const double den = wet ? 1 + sr * th : 1 + (1 - sr) * th;                  // :96 / :108
-            frac = num / den;
-        }
+        const double sr = S / x1;
+        const double th = tanh(arg / x1);
+        const double num = wet ? (x1 * (1 - sr * sr)) * th : (S * (2 - sr)) * th;  // :95 / :107
+        const double den = wet ? 1 + sr * th : 1 + (1 - sr) * th;                  // :96 / :108
+        const double frac = num / den;
         const double p_s = wet ? frac : 0.0;
         const double e_s = wet ? 0.0 : frac;
         S = S - e_s + p_s;  // :114
-        if (MATH == RRB_MATH_FAST_) {
-            const double u = (4.0 / 9.0 * S) * inv_x1;
-            const double u2 = u * u;
-            perc = S * (1 - fast_rsqrt4_ge1(1 + u2 * u2));
-        } else {
-            const double u = 4.0 / 9.0 * S / x1;
-            const double u2 = u * u;
-            perc = S * (1 - pow(1 + u2 * u2, -0.25));  // :117
-        }
+        const double u = 4.0 / 9.0 * S / x1;
+        const double uu = u * u;
+        const double perc = S * (1 - pow(1 + uu * uu, -0.25));  // :117
         S = S - perc;                           // :120
         const double p_r = perc + (p_n - p_s);  // :123
         const double p1 = 0.9 * p_r;            // :126
@@ -125,25 +112,58 @@ struct Gr4jMember {
             u2[j] = (j == n2 - 1) ? add : u2[j + 1] + add;
         }
         u2[C2 - 1] = o2[C2 - 1] * p2;
-        if (MATH == RRB_MATH_FAST_) {
-            const double w = R * inv_x3;
-            gw = x2 * ((w * w) * (w * sqrt(w)));  // w^3.5 (NaN for w < 0, like pow)
-        } else {
-            gw = x2 * pow(R / x3, 3.5);  // :139
-        }
-        R = nb_max0(R + u1[0] + gw);  // :142
-        if (MATH == RRB_MATH_FAST_) {
-            const double v = R * inv_x3;
-            const double v2 = v * v;
-            q_r = R * (1 - fast_rsqrt4_ge1(1 + v2 * v2));
-        } else {
-            const double v = R / x3;
-            const double v2 = v * v;
-            q_r = R * (1 - pow(1 + v2 * v2, -0.25));  // :145
-        }
-        R = R - q_r;                            // :148
+        const double gw = x2 * pow(R / x3, 3.5);  // :139
+        R = nb_max0(R + u1[0] + gw);              // :142
+        const double v = R / x3;
+        const double vv = v * v;
+        const double q_r = R * (1 - pow(1 + vv * vv, -0.25));  // :145
+        R = R - q_r;                             // :148
         const double q_d = nb_max0(u2[0] + gw);  // :151
         return q_r + q_d;                        // :154
+    }
+
+    // FAST: same recurrence, fewer fp64 instructions (every one of them costs two issue slots):
+    //  * tanh(a) = m/(m+2) with m = expm1(2a), so both production-store formulas collapse to
+    //    num*m / (2 + c*m) -- one table-driven expm1 and one branch-free division,
+    //  * reciprocals of x1 / x3 hoisted, (1+u^4)^(-1/4) and w^3.5 from the reciprocal-square-root unit,
+    //  * the unit hydrographs as one FMA per slot.  A padded slot holds 0 * p: identical to the reference
+    //    for finite p (sign of zero aside); a member whose routed water became inf reads NaN instead.
+    __device__ __forceinline__ double step_fast(double P, double E, uint32_t tb) {
+        const bool wet = P >= E;
+        const double arg = fabs(P - E);
+        const double sr = S * inv_x1;
+        const double m = fast_exp2m1_nonneg_smem(arg * k_tanh, tb);
+        double num, c;
+        if (wet) {
+            num = x1 * fma(-sr, sr, 1.0);
+            c = 1.0 + sr;
+        } else {
+            num = S * (2.0 - sr);
+            c = 2.0 - sr;
+        }
+        const double frac = fast_div_pos(num * m, fma(c, m, 2.0));
+        const double dS = wet ? frac : -frac;   // + p_s or - e_s
+        S = S + dS;
+        const double u = S * k49;
+        const double uu = u * u;
+        const double perc = S * (1.0 - fast_rsqrt4_ge1(fma(uu, uu, 1.0)));
+        S = S - perc;
+        const double p_r = wet ? perc + (arg - frac) : perc;
+        const double p1 = 0.9 * p_r;
+        const double p2 = 0.1 * p_r;
+#pragma unroll
+        for (int j = 0; j < C1 - 1; ++j) u1[j] = fma(o1[j], p1, u1[j + 1]);
+        u1[C1 - 1] = o1[C1 - 1] * p1;
+#pragma unroll
+        for (int j = 0; j < C2 - 1; ++j) u2[j] = fma(o2[j], p2, u2[j + 1]);
+        u2[C2 - 1] = o2[C2 - 1] * p2;
+        const double gw = x2 * fast_pow35_nonneg(R * inv_x3);
+        R = nb_max0(R + u1[0] + gw);
+        const double v = R * inv_x3;
+        const double vv = v * v;
+        const double q_r = R * (1.0 - fast_rsqrt4_ge1(fma(vv, vv, 1.0)));
+        R = R - q_r;
+        return q_r + nb_max0(u2[0] + gw);
     }
 };
 
@@ -198,7 +218,7 @@ struct Gr4jMemberDyn {
         for (int j = 0; j < kGr4jGenericC1; ++j) state[(2 + j) * N + i] = u1[j];
         for (int j = 0; j < kGr4jGenericC2; ++j) state[(2 + kGr4jGenericC1 + j) * N + i] = u2[j];
     }
-    __device__ double step(double P, double E, const FastTables*) {
+    __device__ double step(double P, double E, uint32_t) {
         const bool wet = P >= E;
         const double arg = wet ? P - E : E - P;
         const double p_n = wet ? arg : 0.0;

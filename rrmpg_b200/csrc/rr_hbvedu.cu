@@ -63,7 +63,7 @@ struct HbvF {  // forcing of one timestep
 
 // rare operands (soil/FC outside [2^-15, 2^15), |Beta| >= 32, FC <= 0, non-finite values): the reference's
 // own operations, out of line so they cost the time loop one predicated branch
-__device__ __noinline__ double hbv_slow_pow(double soil, double FC, double Beta) { return pow(soil / FC, Beta); }
+static __device__ __noinline__ double hbv_slow_pow(double soil, double FC, double Beta) { return pow(soil / FC, Beta); }
 
 // ------------------------------------------------------------------------------------------------
 // PRECISE: every operation of the reference, in the reference's order.

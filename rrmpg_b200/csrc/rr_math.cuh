@@ -212,18 +212,82 @@ __device__ __forceinline__ PowRegs load_pow_regs(uint32_t tb_addr) {
                    lds_f64_at(c + 32)};
 }
 
-// v^(-1/4) for v >= 1 finite: fp32 SFU seed refined by one third-order step and one Newton step
-// (result within ~1 ulp).  Used for the (1 + u^4)^(-0.25) terms of rrmpg/models/gr4j_model.py:117,145.
+// 2^z - 1 for z >= 0 through the shared-memory tables (device twin of fast_exp2m1_nonneg)
+__device__ __forceinline__ double fast_exp2m1_nonneg_smem(double z, uint32_t tb_addr) {
+    constexpr double C[6] = RRB_EXP2_POLY;
+    constexpr double kShift = 0x1.8p52 / tables::kExpN;
+    z = (z > 64.0) ? 64.0 : z;
+    double kd = z + kShift;
+    const uint32_t ki = (uint32_t)__double2loint(kd);
+    kd -= kShift;
+    const double r = z - kd;
+    const uint32_t j8 = (ki & (tables::kExpN - 1)) * 8u;
+    uint32_t tlo, thi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                 : "=r"(tlo), "=r"(thi)
+                 : "r"(tb_addr + (uint32_t)offsetof(FastTables, exp2tab) + j8));
+    const double scale = __hiloint2double((int)(thi + (ki << 13)), (int)tlo);
+    double m1;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(m1) : "r"(tb_addr + (uint32_t)offsetof(FastTables, exp2m1tab) + j8));
+    const double base = (ki < (uint32_t)tables::kExpN) ? m1 : scale - 1.0;
+    const double r2 = r * r;
+    const double a = fma(r, C[1], C[0]);
+    double b = fma(r, C[3], C[2]);
+    b = fma(r2, C[4], b);
+    const double t = fma(r2, b, a);
+    return fma(scale, r * t, base);
+}
+
+// num / den for a normal, positive, comfortably ranged den (here den in [2, ~4]): reciprocal seed
+// refined by two Newton steps and one residual correction -- correctly rounded in practice, no
+// special-case branches (the IEEE division sequence carries a slow-path call)
+__device__ __forceinline__ double fast_div_pos(double num, double den) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+    double e = fma(-den, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-den, y, 1.0);
+    y = fma(y, e, y);
+    const double q = num * y;
+    const double r = fma(-den, q, num);
+    return fma(r, y, q);
+}
+
+// v^(-1/4) for finite v >= 1, used for the (1 + u^4)^(-0.25) terms of rrmpg/models/gr4j_model.py:117,145.
+// Seed from the fp64 reciprocal-square-root unit applied twice (rsq(v) * rsq(rsq(v)) = v^-1/2 * v^1/4),
+// one third-order and one Newton refinement: within ~1 ulp, no conversions, no special-case branch.
+// Non-finite / NaN operands take libm.
+__device__ __forceinline__ double rsqrt_approx_f64(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    return y;
+}
 __device__ __forceinline__ double fast_rsqrt4_ge1(double v) {
-    if (!(v < 1e30)) return pow(v, -0.25);  // inf / nan / huge: keep libm semantics
-    const float vf = (float)v;
-    double y = (double)rsqrtf(sqrtf(vf));            // ~2^-22
+    if (!(v < 1e300)) return pow(v, -0.25);  // inf / nan: keep libm semantics
+    const double a = rsqrt_approx_f64(v);
+    double y = a * rsqrt_approx_f64(a);               // ~2^-19 relative
     double y2 = y * y;
-    double e = fma(-v, y2 * y2, 1.0);                // 1 - v y^4
-    y = fma(y, e * fma(e, 0.15625, 0.25), y);        // y (1 + e/4 + 5 e^2/32): error ~ e^3
+    double e = fma(-v, y2 * y2, 1.0);                 // 1 - v y^4
+    y = fma(y, e * fma(e, 0.15625, 0.25), y);         // y (1 + e/4 + 5 e^2/32): error ~ e^3
     y2 = y * y;
     e = fma(-v, y2 * y2, 1.0);
     return fma(y * 0.25, e, y);
+}
+
+// w^3.5 for w >= 0 (NaN for w < 0, like pow): w^4 * w^(-1/2), the reciprocal square root from the seed unit
+// plus two Newton steps.  w == 0 and non-finite w go through exact selects.
+__device__ __forceinline__ double fast_pow35_nonneg(double w) {
+    double y = rsqrt_approx_f64(w);
+    double t = w * y;
+    double e = fma(-t, y, 1.0);        // 1 - w y^2
+    y = fma(0.5 * y, e, y);
+    t = w * y;
+    e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    const double w2 = w * w;
+    const double r = (w2 * w2) * y;
+    // w = 0 -> 0 (the seed is inf there); w = inf -> inf; w < 0 or NaN -> NaN comes out of the seed
+    return (w == 0.0) ? 0.0 : ((w > 1e300) ? w : r);
 }
 
 // stage the tables into shared memory (call by every thread, before a __syncthreads())
