@@ -268,6 +268,7 @@ def main():
                "api": "rrmpg_b200.models.HBVEdu.simulate(numpy) -> numpy [T, N] (pinned), D2H pipelined per time slab"}
 
     if rank != 0:
+        rdist.shutdown()
         return 0
 
     peak, peak_src = measured_peaks()
@@ -294,6 +295,7 @@ def main():
     line["config"]["math"] = args.math
     line["config"]["members_per_gpu"] = members
     print(json.dumps(line), flush=True)
+    rdist.shutdown()
     return 0
 
 

@@ -124,6 +124,16 @@ RRB_API int rrb_hbvedu_simulate(const double* temp, const double* prec, const in
                         double* qsim, double* snow, double* soil, double* s1, double* s2 /* nullable x4 */,
                         const rrb_opts* opts);
 
+/* HBV-Edu for C independent catchments that share T and the ensemble size N (the
+ * reference has no batched equivalent -- a user loops HBVEdu.simulate over basins).  temp, prec, month0:
+ * [C, T]; PE_m, T_m: [C, 12]; inits: host [C, 4]; params: [C, N, 11]; outputs [C, T, N]; opts->qobs [C, T] and
+ * opts->mse [C, N].  One kernel launch covers every catchment (grid.y = catchment); with host buffers the
+ * catchments are processed in chunks whose D2H overlaps the next chunk's kernel. */
+RRB_API int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
+                                      const double* T_m, int64_t C, int64_t T, const double* inits,
+                                      const double* params, int64_t N, double* qsim, double* snow, double* soil,
+                                      double* s1, double* s2 /* nullable x4 */, const rrb_opts* opts);
+
 /* GR4J.  s_init, r_init are fractions of x1 / x3 (gr4j_model.py:64-65).  params[N][4] =
  * (x1, x2, x3, x4).  Every member is simulated (the reference returns after member 0 when
  * return_storage=False, gr4j.py:178 -- a bug this API does not reproduce). */

@@ -44,6 +44,8 @@ _SIGS = {
                                    C.c_void_p, C.c_void_p, C.POINTER(Opts)]),
     "rrb_hbvedu_simulate": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
                             + [C.c_void_p] * 5 + [C.POINTER(Opts)]),
+    "rrb_hbvedu_simulate_multi": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
+                                  + [C.c_void_p] * 5 + [C.POINTER(Opts)]),
     "rrb_gr4j_simulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(Opts)]),

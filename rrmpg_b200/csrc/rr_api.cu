@@ -546,7 +546,7 @@ int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* mo
     memcpy(in4, inits, sizeof(in4));  // inits is host memory in both modes
     void* F;
     if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, kHbvTT) * kHbvR, &F))) return rc;
-    RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.o.math, P.s));
+    RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.o.math, 1, P.s));
     Job job;
     job.T = T; job.N = N;
     job.outs = {{qsim, N}, {snow, N}, {soil, N}, {s1, N}, {s2, N}};
@@ -558,6 +558,108 @@ int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* mo
         return launch_hbvedu((const double*)F, T, in, dp, N, out[0], out[1], out[2], out[3], out[4], sl, ob, cfg);
     };
     return run_job(*P.c, P.o, job, P.d_qobs, P.d_mse);
+}
+
+// ---- HBV-Edu, C catchments in one launch ----
+int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
+                              const double* T_m, int64_t C, int64_t T, const double* inits, const double* params,
+                              int64_t N, double* qsim, double* snow, double* soil, double* s1, double* s2,
+                              const rrb_opts* opts) {
+    Prepared P;
+    int rc = prepare(opts, T, N, params, 11, &P);
+    if (rc) return rc;
+    if (C < 0) return fail(RRB_EINVAL, "C = %lld", (long long)C);
+    if (!temp || !prec || !month0 || !PE_m || !T_m || !inits) return fail(RRB_EINVAL, "NULL forcing / inits pointer");
+    const int nst = (snow != nullptr) + (soil != nullptr) + (s1 != nullptr) + (s2 != nullptr);
+    if (nst != 0 && nst != 4) return fail(RRB_EINVAL, "pass all four storage outputs or none");
+    if (!qsim && !P.o.qobs && nst == 0) return fail(RRB_EINVAL, "nothing to compute");
+    if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
+    if (N == 0 || C == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    Ctx& c = *P.c;
+    const bool host = P.o.mem == RRB_MEM_HOST;
+    const double *d_temp, *d_prec, *d_pe, *d_tm;
+    const int8_t* d_month;
+    if ((rc = stage_in(c, P.o, B_RAW0, temp, (size_t)(C * T), &d_temp))) return rc;
+    if ((rc = stage_in(c, P.o, B_RAW1, prec, (size_t)(C * T), &d_prec))) return rc;
+    if ((rc = stage_in(c, P.o, B_RAW2, month0, (size_t)(C * T), &d_month))) return rc;
+    if ((rc = stage_in(c, P.o, B_RAW3, PE_m, (size_t)(C * 12), &d_pe))) return rc;
+    if ((rc = stage_in(c, P.o, B_RAW4, T_m, (size_t)(C * 12), &d_tm))) return rc;
+    if ((rc = stage_in(c, P.o, B_PARAMS, params, (size_t)(C * N * 11), &P.d_params))) return rc;
+    // per-catchment initial states: always host memory -> small device array
+    void* d_inits;
+    if ((rc = c.ensure(B_SCALAR, sizeof(double) * 4 * (size_t)C, &d_inits))) return rc;
+    RRB_CUDA(cudaMemcpyAsync(d_inits, inits, sizeof(double) * 4 * (size_t)C, cudaMemcpyHostToDevice, P.s));
+    if (P.o.qobs) {
+        if ((rc = stage_in(c, P.o, B_QOBS, P.o.qobs, (size_t)(C * T), &P.d_qobs))) return rc;
+        if (host) {
+            void* p;
+            if ((rc = c.ensure(B_MSE, sizeof(double) * (size_t)(C * N), &p))) return rc;
+            P.d_mse = (double*)p;
+        } else {
+            P.d_mse = P.o.mse;
+        }
+    }
+    const int64_t Tpad = padded_steps(T, kHbvTT);
+    void* F;
+    if ((rc = c.ensure(B_F, sizeof(double) * (size_t)(C * Tpad) * kHbvR, &F))) return rc;
+    RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.o.math, (int)C, P.s));
+
+    LaunchCfg cfg{};
+    cfg.block = P.o.block;
+    cfg.math = P.o.math;
+    cfg.sm_count = c.sm_count;
+    cfg.stream = P.s;
+    const double zero4[4] = {0, 0, 0, 0};
+    double* outs[5] = {qsim, snow, soil, s1, s2};
+
+    if (!host) {
+        Batch b{(int)C, Tpad * kHbvR, T * N, (const double*)d_inits};
+        Slab slab{0, T, 0, nullptr, 0};
+        Objective obj{P.d_qobs, P.d_mse, T};
+        RRB_CUDA(launch_hbvedu((const double*)F, T, zero4, P.d_params, N, qsim, snow, soil, s1, s2, slab, obj, cfg, b));
+        return RRB_OK;
+    }
+    // host buffers: chunks of catchments through a two-deep device ring; the D2H of chunk k overlaps the
+    // kernel of chunk k+1 (each chunk is a contiguous [cc, T, N] block of every output)
+    int64_t bytes_per_catchment = 0;
+    for (double* o : outs)
+        if (o) bytes_per_catchment += T * N * (int64_t)sizeof(double);
+    int64_t cc = C;
+    if (bytes_per_catchment > 0) cc = std::max<int64_t>(1, std::min<int64_t>(C, (int64_t)(kSlabTargetBytes * 2) / bytes_per_catchment));
+    const int nchunks = (int)((C + cc - 1) / cc);
+    double* dev[2][5] = {};
+    for (int sidx = 0; sidx < (nchunks > 1 ? 2 : 1); ++sidx)
+        for (int k = 0; k < 5; ++k)
+            if (outs[k]) {
+                void* p;
+                if ((rc = c.ensure(B_OUT0 + 2 * k + sidx, sizeof(double) * (size_t)(cc * T * N), &p))) return rc;
+                dev[sidx][k] = (double*)p;
+            }
+    for (int k = 0; k < nchunks; ++k) {
+        const int sidx = k & 1;
+        const int64_t c0 = (int64_t)k * cc, c1 = std::min(C, c0 + cc);
+        if (k >= 2) RRB_CUDA(cudaStreamWaitEvent(c.compute, c.ev_free[sidx], 0));
+        Batch b{(int)(c1 - c0), Tpad * kHbvR, T * N, (const double*)d_inits + 4 * c0};
+        Slab slab{0, T, 0, nullptr, 0};
+        Objective obj{P.d_qobs ? P.d_qobs + c0 * T : nullptr, P.d_mse ? P.d_mse + c0 * N : nullptr, T};
+        RRB_CUDA(launch_hbvedu((const double*)F + c0 * Tpad * kHbvR, T, zero4, P.d_params + c0 * N * 11, N, dev[sidx][0],
+                               dev[sidx][1], dev[sidx][2], dev[sidx][3], dev[sidx][4], slab, obj, cfg, b));
+        RRB_CUDA(cudaEventRecord(c.ev_done[sidx], c.compute));
+        RRB_CUDA(cudaStreamWaitEvent(c.copy, c.ev_done[sidx], 0));
+        for (int j = 0; j < 5; ++j)
+            if (outs[j])
+                RRB_CUDA(cudaMemcpyAsync(outs[j] + (size_t)(c0 * T * N), dev[sidx][j],
+                                         sizeof(double) * (size_t)((c1 - c0) * T * N), cudaMemcpyDeviceToHost, c.copy));
+        RRB_CUDA(cudaEventRecord(c.ev_free[sidx], c.copy));
+    }
+    if (P.o.qobs) {
+        RRB_CUDA(cudaStreamWaitEvent(c.copy, c.ev_done[(nchunks - 1) & 1], 0));
+        RRB_CUDA(cudaMemcpyAsync(P.o.mse, P.d_mse, sizeof(double) * (size_t)(C * N), cudaMemcpyDeviceToHost, c.copy));
+    }
+    RRB_CUDA(cudaStreamSynchronize(c.copy));
+    RRB_CUDA(cudaStreamSynchronize(c.compute));
+    return RRB_OK;
 }
 
 // ---- GR4J ----

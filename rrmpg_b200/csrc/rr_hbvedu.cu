@@ -29,6 +29,9 @@ __global__ void hbv_pack_kernel(const double* __restrict__ temp, const double* _
                                 double* __restrict__ F) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= Tpad) return;
+    const int64_t c = blockIdx.y;  // catchment
+    temp += c * T; prec += c * T; month0 += c * T; PE_m += c * 12; T_m += c * 12;
+    F += c * Tpad * kHbvR;
     double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
     if (t < T) {
         const int m = month0[t];
@@ -42,16 +45,34 @@ __global__ void hbv_pack_kernel(const double* __restrict__ temp, const double* _
 }
 
 cudaError_t pack_hbvedu(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
-                        const double* T_m, int64_t T, double* F, int math, cudaStream_t s) {
+                        const double* T_m, int64_t T, double* F, int math, int count, cudaStream_t s) {
     int64_t Tpad = padded_steps(T, kHbvTT);
-    hbv_pack_kernel<<<(unsigned)((Tpad + 255) / 256), 256, 0, s>>>(temp, prec, month0, PE_m, T_m, T, Tpad,
-                                                                   math == RRB_MATH_FAST_, F);
+    hbv_pack_kernel<<<dim3((unsigned)((Tpad + 255) / 256), (unsigned)count), 256, 0, s>>>(temp, prec, month0, PE_m, T_m, T,
+                                                                                      Tpad, math == RRB_MATH_FAST_, F);
     return cudaGetLastError();
 }
 
 struct HbvOut {
     double *qsim, *snow, *soil, *s1, *s2;
 };
+
+// blockIdx.y = catchment: shift every per-catchment pointer (a no-op for the single-catchment launch)
+#define HBV_BATCH_PROLOGUE                                                        \
+    if (batch.count > 1) {                                                        \
+        const int64_t c = blockIdx.y;                                             \
+        F += c * batch.forcing_stride;                                            \
+        params += c * N * 11;                                                     \
+        if (out.qsim) out.qsim += c * batch.out_stride;                           \
+        if (out.snow) {                                                           \
+            out.snow += c * batch.out_stride; out.soil += c * batch.out_stride;   \
+            out.s1 += c * batch.out_stride; out.s2 += c * batch.out_stride;       \
+        }                                                                         \
+        if (obj.qobs) { obj.qobs += c * obj.T; obj.mse += c * N; }                \
+        if (batch.inits) {                                                        \
+            snow0 = batch.inits[4 * c]; soil0 = batch.inits[4 * c + 1];           \
+            s10 = batch.inits[4 * c + 2]; s20 = batch.inits[4 * c + 3];           \
+        }                                                                         \
+    }
 
 struct HbvF {  // forcing of one timestep
     double temp, prec, dT, PEm;
@@ -71,7 +92,8 @@ static __device__ __noinline__ double hbv_slow_pow(double soil, double FC, doubl
 template <bool WRITEQ, bool STORAGE, bool OBJ>
 __global__ void hbv_precise_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                                    const double* __restrict__ params, int64_t N, HbvOut out, Slab slab,
-                                   Objective obj) {
+                                   Objective obj, Batch batch) {
+    HBV_BATCH_PROLOGUE
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     // threads past the end of the ensemble recompute member N-1 and store the same values to the same
     // addresses: no predicate lives in the time loop
@@ -186,7 +208,8 @@ constexpr int kHbvGroup = RRB_HBV_GROUP;
 template <bool WRITEQ, bool STORAGE, bool OBJ>
 __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                                 const double* __restrict__ params, int64_t N, HbvOut out, Slab slab,
-                                Objective obj) {
+                                Objective obj, Batch batch) {
+    HBV_BATCH_PROLOGUE
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t i = gi < N ? gi : N - 1;  // see hbv_precise_kernel
     const double* p = params + 11 * i;
@@ -335,18 +358,18 @@ int state_slots_hbvedu() { return 5; }
 
 cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, const double* params, int64_t N,
                           double* qsim, double* snow, double* soil, double* s1, double* s2, const Slab& slab,
-                          const Objective& obj, const LaunchCfg& cfg) {
+                          const Objective& obj, const LaunchCfg& cfg, const Batch& batch) {
     (void)T;
-    if (N <= 0) return cudaSuccess;
-    const int block = cfg.block > 0 ? cfg.block : pick_block(N, cfg.sm_count, 256);
-    const unsigned grid = (unsigned)((N + block - 1) / block);
+    if (N <= 0 || batch.count <= 0) return cudaSuccess;
+    const int block = cfg.block > 0 ? cfg.block : pick_block(N * batch.count, cfg.sm_count, N >= 256 ? 256 : 64);
+    const dim3 grid((unsigned)((N + block - 1) / block), (unsigned)batch.count);
     const bool fast = cfg.math == RRB_MATH_FAST_;
     const size_t smem = forcing_smem_bytes<kHbvR, kHbvTT>() + (fast ? fastmath_smem_bytes() : 0);
     const bool st = snow != nullptr, ob = obj.qobs != nullptr, wq = qsim != nullptr;
     HbvOut out{qsim, snow, soil, s1, s2};
 #define RRB_HBV(M_, Q_, S_, O_)                                                                                   \
     M_<Q_, S_, O_><<<grid, block, smem, cfg.stream>>>(F, inits4[0], inits4[1], inits4[2], inits4[3], params, N, out, \
-                                                      slab, obj)
+                                                      slab, obj, batch)
 #define RRB_HBV_M(M_)                                      \
     do {                                                   \
         if (wq && st && ob) RRB_HBV(M_, true, true, true);        \

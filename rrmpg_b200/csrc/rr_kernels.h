@@ -18,6 +18,16 @@ struct Slab {
     int save_state;
 };
 
+// Catchment batching: blockIdx.y selects one of `count` independent catchments that share T and the
+// number of members N.  Element strides (in doubles) between consecutive catchments; count = 1 and zero
+// strides describe the ordinary single-catchment call.
+struct Batch {
+    int count;
+    int64_t forcing_stride;  // packed forcing: Tpad * R
+    int64_t out_stride;      // every [T, N] output: T * N
+    const double* inits;     // optional device array [count][4] of per-catchment initial states (nullable)
+};
+
 struct LaunchCfg {
     cudaStream_t stream;
     int block;  // threads per CTA (0 = auto from N and the SM count)
@@ -52,8 +62,9 @@ inline int64_t padded_steps(int64_t T, int TT) { return ((T + TT - 1) / TT) * TT
 
 // ---- forcing packers (device pointers in, packed F[Tpad][R] out) ----
 cudaError_t pack_abc(const double* prec, int64_t T, double* F, cudaStream_t s);
+// count catchments: inputs are [count][T] (PE_m, T_m: [count][12]), F is [count][Tpad][R]
 cudaError_t pack_hbvedu(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
-                        const double* T_m, int64_t T, double* F, int math, cudaStream_t s);
+                        const double* T_m, int64_t T, double* F, int math, int count, cudaStream_t s);
 cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* F, cudaStream_t s);
 // writes F and g_tresh[L] (sequential np.mean semantics, rrmpg/models/cemaneige_model.py:80)
 cudaError_t pack_cemaneige(const double* prec, const double* mean_temp, const double* frac, const double* etp,
@@ -65,7 +76,7 @@ cudaError_t launch_abc(const double* F, int64_t T, double s0, const double* para
 
 cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, const double* params, int64_t N,
                           double* qsim, double* snow, double* soil, double* s1, double* s2, const Slab& slab,
-                          const Objective& obj, const LaunchCfg& cfg);
+                          const Objective& obj, const LaunchCfg& cfg, const Batch& batch = Batch{1, 0, 0, nullptr});
 
 // uh_cap: 0 = derive from x4_max
 cudaError_t launch_gr4j(const double* F, int64_t T, double s_init, double r_init, const double* params,

@@ -136,6 +136,14 @@ class _Call:
             self.opts.mse = _lib.ptr(self.mse)
 
 
+def _run(call, T, N, fn, *args):
+    """Call the library unless the problem is empty (T == 0 or N == 0: nothing to simulate)."""
+    if T > 0 and N > 0:
+        _lib.check(fn(*args))
+    elif call.mse is not None and N > 0:
+        call.mse[...] = float("nan")  # np.mean over an empty series (rrmpg/utils/metrics.py:131)
+
+
 def _result(call, names, arrays):
     out = {n: a for n, a in zip(names, arrays) if a is not None}
     if call.mse is not None:
@@ -156,8 +164,8 @@ def abc(prec, initial_state, params, return_storage=False, qobs=None, want_qsim=
     q = c.empty((T, N), out.get("qsim")) if want_qsim else None
     s = c.empty((T, N), out.get("storage")) if return_storage else None
     c.want_mse(N, T)
-    _lib.check(_lib.lib().rrb_abc_simulate(_lib.ptr(prec), T, float(initial_state), _lib.ptr(P), N,
-                                           _lib.ptr(q), _lib.ptr(s), C.byref(c.opts)))
+    _run(c, T, N, _lib.lib().rrb_abc_simulate, _lib.ptr(prec), T, float(initial_state), _lib.ptr(P), N,
+         _lib.ptr(q), _lib.ptr(s), C.byref(c.opts))
     return _result(c, ["qsim", "storage"], [q, s])
 
 
@@ -182,9 +190,52 @@ def hbvedu(temp, prec, month0, PE_m, T_m, inits, params, return_storage=False, q
     names = ["snow", "soil", "s1", "s2"]
     st = [c.empty((T, N), out.get(n)) for n in names] if return_storage else [None] * 4
     c.want_mse(N, T)
-    _lib.check(_lib.lib().rrb_hbvedu_simulate(
-        _lib.ptr(temp), _lib.ptr(prec), _lib.ptr(month0), _lib.ptr(PE_m), _lib.ptr(T_m), T,
-        _lib.ptr(inits), _lib.ptr(P), N, _lib.ptr(q), *[_lib.ptr(a) for a in st], C.byref(c.opts)))
+    _run(c, T, N, _lib.lib().rrb_hbvedu_simulate,
+         _lib.ptr(temp), _lib.ptr(prec), _lib.ptr(month0), _lib.ptr(PE_m), _lib.ptr(T_m), T,
+         _lib.ptr(inits), _lib.ptr(P), N, _lib.ptr(q), *[_lib.ptr(a) for a in st], C.byref(c.opts))
+    return _result(c, ["qsim"] + names, [q] + st)
+
+
+def hbvedu_multi(temp, prec, month0, PE_m, T_m, inits, params, return_storage=False, qobs=None, want_qsim=True,
+                 math=DEFAULT_MATH, device=None, block=0, out=None):
+    """HBV-Edu for C independent catchments with N members each, one launch.
+
+    temp, prec, month0: [C, T]; PE_m, T_m: [C, 12]; inits: (4,) or [C, 4]; params: [C, N, 11] (or a [C, N]
+    record array); qobs: [C, T].  Returns {'qsim': [C, T, N], storages..., 'mse': [C, N]}.
+    Equivalent to looping ``hbvedu`` over the catchments (tests/test_parity_gpu.py).
+    """
+    if not _is_torch(params):
+        params = np.asarray(params)
+        if params.dtype.names:
+            Cn, Nn = params.shape
+            params = pack_params(params.reshape(-1)).reshape(Cn, Nn, -1)
+    c = _Call([temp, prec, month0, PE_m, T_m, params], math, device, block, 0, None)
+    temp = c.f64(temp); prec = c.f64(prec); month0 = c.i8(month0); PE_m = c.f64(PE_m); T_m = c.f64(T_m)
+    P = c.f64(params)
+    if temp.ndim != 2 or P.ndim != 3 or P.shape[2] != 11:
+        raise ValueError("expected temp/prec/month0 [C, T] and params [C, N, 11]")
+    (Cc, T), N = temp.shape, P.shape[1]
+    for a, shp in ((prec, (Cc, T)), (month0, (Cc, T)), (PE_m, (Cc, 12)), (T_m, (Cc, 12))):
+        if tuple(a.shape) != shp:
+            raise ValueError(f"array of shape {tuple(a.shape)}, expected {shp}")
+    if P.shape[0] != Cc:
+        raise ValueError("params must have one [N, 11] block per catchment")
+    ini = np.asarray(inits, dtype=np.float64)
+    ini = np.ascontiguousarray(np.broadcast_to(ini.reshape(-1, 4), (Cc, 4)))
+    c.keep.append(ini)
+    if qobs is not None:
+        q_ = c.f64(qobs, (Cc, T))
+        c.opts.qobs = _lib.ptr(q_)
+        c.mse = c.empty((Cc, N))
+        c.opts.mse = _lib.ptr(c.mse)
+    out = out or {}
+    q = c.empty((Cc, T, N), out.get("qsim")) if want_qsim else None
+    names = ["snow", "soil", "s1", "s2"]
+    st = [c.empty((Cc, T, N), out.get(n)) for n in names] if return_storage else [None] * 4
+    if Cc > 0 and T > 0:
+        _lib.check(_lib.lib().rrb_hbvedu_simulate_multi(
+            _lib.ptr(temp), _lib.ptr(prec), _lib.ptr(month0), _lib.ptr(PE_m), _lib.ptr(T_m), Cc, T, _lib.ptr(ini),
+            _lib.ptr(P), N, _lib.ptr(q), *[_lib.ptr(a) for a in st], C.byref(c.opts)))
     return _result(c, ["qsim"] + names, [q] + st)
 
 
@@ -211,9 +262,8 @@ def gr4j(prec, etp, s_init, r_init, params, return_storage=False, qobs=None, wan
     names = ["s_store", "r_store"]
     st = [c.empty((T, N), out.get(n)) for n in names] if return_storage else [None] * 2
     c.want_mse(N, T)
-    _lib.check(_lib.lib().rrb_gr4j_simulate(_lib.ptr(prec), _lib.ptr(etp), T, float(s_init), float(r_init),
-                                            _lib.ptr(P), N, _lib.ptr(q), _lib.ptr(st[0]), _lib.ptr(st[1]),
-                                            C.byref(c.opts)))
+    _run(c, T, N, _lib.lib().rrb_gr4j_simulate, _lib.ptr(prec), _lib.ptr(etp), T, float(s_init), float(r_init),
+         _lib.ptr(P), N, _lib.ptr(q), _lib.ptr(st[0]), _lib.ptr(st[1]), C.byref(c.opts))
     return _result(c, ["qsim"] + names, [q] + st)
 
 
@@ -239,10 +289,10 @@ def cemaneige(prec, mean_temp, frac_solid, snow_pack_init, thermal_state_init, p
     names = ["G", "eTG"]
     st = [c.empty((T, L, N), out.get(n)) for n in names] if return_storages else [None] * 2
     c.want_mse(N, T)
-    _lib.check(_lib.lib().rrb_cemaneige_simulate(
-        _lib.ptr(prec), _lib.ptr(mean_temp), _lib.ptr(frac_solid), T, L, float(snow_pack_init),
-        float(thermal_state_init), _lib.ptr(P), P.shape[1], N, _lib.ptr(q), _lib.ptr(st[0]),
-        _lib.ptr(st[1]), C.byref(c.opts)))
+    _run(c, T, N, _lib.lib().rrb_cemaneige_simulate,
+         _lib.ptr(prec), _lib.ptr(mean_temp), _lib.ptr(frac_solid), T, L, float(snow_pack_init),
+         float(thermal_state_init), _lib.ptr(P), P.shape[1], N, _lib.ptr(q), _lib.ptr(st[0]),
+         _lib.ptr(st[1]), C.byref(c.opts))
     return _result(c, ["outflow"] + names, [q] + st)
 
 
@@ -272,7 +322,7 @@ def cemaneigegr4j(prec, mean_temp, etp, frac_solid, inits, params, return_storag
     s = c.empty((T, N), out.get("s_store")) if return_storages else None
     r = c.empty((T, N), out.get("r_store")) if return_storages else None
     c.want_mse(N, T)
-    _lib.check(_lib.lib().rrb_cemaneigegr4j_simulate(
-        _lib.ptr(prec), _lib.ptr(mean_temp), _lib.ptr(etp), _lib.ptr(frac_solid), T, L, _lib.ptr(inits),
-        _lib.ptr(P), N, _lib.ptr(q), _lib.ptr(G), _lib.ptr(E), _lib.ptr(s), _lib.ptr(r), C.byref(c.opts)))
+    _run(c, T, N, _lib.lib().rrb_cemaneigegr4j_simulate,
+         _lib.ptr(prec), _lib.ptr(mean_temp), _lib.ptr(etp), _lib.ptr(frac_solid), T, L, _lib.ptr(inits),
+         _lib.ptr(P), N, _lib.ptr(q), _lib.ptr(G), _lib.ptr(E), _lib.ptr(s), _lib.ptr(r), C.byref(c.opts))
     return _result(c, ["qsim", "G", "eTG", "s_store", "r_store"], [q, G, E, s, r])

@@ -329,3 +329,54 @@ def test_full_size_hbvedu_properties():
     assert_close(q[:, idx], ref, "hbvedu 65k sampled columns")
     sub = engine.hbvedu(f["temp"], f["prec"], m0, f["PE_m"], f["T_m"], (0, 100, 3, 10), P[idx])["qsim"]
     assert_bits_equal(sub, q[:, idx], "batch independence")
+
+
+# ------------------------------------------------------------------ multi-catchment batch, fit(), empty inputs
+def test_multi_catchment_equals_a_loop_over_catchments():
+    Cn, T, N = 5, 400, 70
+    fs = [synthetic.forcing(T, seed=100 + c) for c in range(Cn)]
+    P = np.stack([engine.pack_params(synthetic.random_params(HBVEdu(), N, seed=200 + c)) for c in range(Cn)])
+    temp = np.stack([f["temp"] for f in fs]); prec = np.stack([f["prec"] for f in fs])
+    m0 = np.stack([f["month"] - 1 for f in fs]).astype(np.int8)
+    PE = np.stack([f["PE_m"] * (1 + 0.1 * c) for c, f in enumerate(fs)]); TM = np.stack([f["T_m"] - c for c, f in enumerate(fs)])
+    inits = np.array([[c, 100 + 5 * c, 3, 10] for c in range(Cn)], float)
+    qobs = np.abs(np.random.default_rng(3).normal(1.0, 0.5, (Cn, T)))
+    multi = engine.hbvedu_multi(temp, prec, m0, PE, TM, inits, P, return_storage=True, qobs=qobs)
+    assert multi["qsim"].shape == (Cn, T, N) and multi["mse"].shape == (Cn, N)
+    for c in range(Cn):
+        one = engine.hbvedu(temp[c], prec[c], m0[c], PE[c], TM[c], inits[c], P[c], return_storage=True, qobs=qobs[c])
+        for nm in one:
+            assert_bits_equal(multi[nm][c], one[nm], f"catchment {c} {nm}")
+        assert_close(multi["qsim"][c], oracle.hbvedu(temp[c], prec[c], m0[c], PE[c], TM[c], inits[c], P[c]), f"catchment {c}")
+    import torch  # device mode, objective only (the only feasible mode for BASELINE config 5)
+    dev = torch.device("cuda:0")
+    t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    r = engine.hbvedu_multi(t(temp), t(prec), t(m0, torch.int8), t(PE), t(TM), inits, t(P), qobs=t(qobs), want_qsim=False)
+    torch.cuda.synchronize()
+    assert set(r) == {"mse"}
+    assert_bits_equal(r["mse"].cpu().numpy(), multi["mse"], "device-mode objective")
+
+
+def test_fit_is_population_vectorised_and_finds_the_generating_parameters():
+    f = synthetic.forcing(600)
+    truth = {'a': 0.3, 'b': 0.25, 'c': 0.12}
+    qobs = ABCModel(params=truth).simulate(f["prec"], initial_state=2.0).flatten()
+    res = ABCModel().fit(qobs, f["prec"], initial_state=2.0)
+    assert res.success and res.fun < 1e-10
+    np.testing.assert_allclose(res.x, [truth['a'], truth['b'], truth['c']], atol=1e-4)
+    truth = dict(zip(GR4J._param_list, [350.0, 0.8, 90.0, 1.7]))
+    qobs = GR4J(params=truth).simulate(f["prec"], f["etp"], s_init=0.5, r_init=0.5).flatten()
+    from rrmpg_b200.models import gr4j as gr4j_mod
+    X = np.array([[350.0, 300.0], [0.8, 1.0], [90.0, 80.0], [1.7, 2.0]])  # (k, S) trial matrix as scipy passes it
+    loss = gr4j_mod._loss(X, qobs, f["prec"], f["etp"], 0.5, 0.5, GR4J._dtype)
+    assert loss.shape == (2,) and loss[0] < 1e-20 and loss[1] > 1e-3
+    assert isinstance(gr4j_mod._loss(X[:, 0], qobs, f["prec"], f["etp"], 0.5, 0.5, GR4J._dtype), float)
+
+
+def test_empty_series_and_empty_ensembles():
+    P = synthetic.random_params(GR4J(), 4)
+    q = GR4J().simulate([], [], params=P)
+    assert q.shape == (0, 4)
+    r = engine.hbvedu(np.zeros(5), np.zeros(5), np.zeros(5, np.int8), np.zeros(12), np.zeros(12), (0, 0, 0, 0),
+                      np.zeros((0, 11)))
+    assert r["qsim"].shape == (5, 0)
