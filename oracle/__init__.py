@@ -46,6 +46,7 @@ def lib():
         _lib.oracle_num_threads.restype = C.c_int
         _lib.oracle_gr4j_batch.restype = C.c_int
         _lib.oracle_cemaneigegr4j_batch.restype = C.c_int
+        _lib.oracle_snowice_gr4j_batch.restype = C.c_int
     return _lib
 
 
@@ -151,6 +152,37 @@ def cemaneigegr4j(prec, mean_temp, etp, frac_solid, inits, params, return_storag
     if rc:
         raise RuntimeError("oracle_cemaneigegr4j: unit hydrograph length out of range")
     return (q, G, E, s, r) if return_storages else q
+
+
+def snowice_gr4j(hyst, ice, prec, mean_temp, etp, frac_ice, frac_solid, inits, params, return_storages=False,
+                 nthreads=0):
+    """The snow(+hysteresis)(+ice)+GR4J couplings over an ensemble.
+
+    hyst=0, ice=1: run_cemaneigegr4jice (rrmpg/models/cemaneigegr4jice_model.py:16-93), records of 7 fields;
+    hyst=1, ice=0: run_cemaneigehystgr4j (cemaneigehystgr4j_model.py:17-79), 8 fields;
+    hyst=1, ice=1: run_cemaneigehystgr4jice (cemaneigehystgr4jice_model.py:18-104), 9 fields.
+    ``inits`` = (snow_pack_init, thermal_state_init, sca_init, s_init, r_init).
+    Returns qsim or (qsim, G, eTG, s_store, r_store, sca, icemelt, snowmelt, rain[T,L]).
+    """
+    prec = _f64(prec); mean_temp = _f64(mean_temp); frac_solid = _f64(frac_solid); etp = _f64(etp)
+    inits = _f64(inits); P = pack_params(params); (T, L), N = prec.shape, P.shape[0]
+    fice = _f64(frac_ice) if frac_ice is not None else np.zeros(L)
+    assert P.shape[1] == 6 + (2 if hyst else 0) + (1 if ice else 0) and inits.size == 5
+    q = np.zeros((T, N))
+    G = E = S = s = r = im = sm = None
+    if return_storages:
+        G, E, S = (np.zeros((T, L, N)) for _ in range(3))
+        s, r, im, sm = (np.zeros((T, N)) for _ in range(4))
+    rc = lib().oracle_snowice_gr4j_batch(C.c_int(int(hyst)), C.c_int(int(ice)), _d(prec), _d(mean_temp), _d(etp),
+                                         _d(fice), _d(frac_solid), C.c_int64(T), C.c_int64(L), _d(inits), _d(P),
+                                         C.c_int64(N), _d(q), _d(G), _d(E), _d(S), _d(s), _d(r), _d(im), _d(sm),
+                                         C.c_int(nthreads))
+    if rc:
+        raise RuntimeError("oracle_snowice_gr4j: unit hydrograph length out of range")
+    if not return_storages:
+        return q
+    rain = prec - prec * frac_solid  # cemaneigehyst_model.py:98-99 (member independent)
+    return q, G, E, s, r, S, im, sm, rain
 
 
 def extrapolate_precipitation(prec, altitudes, met_station_height):

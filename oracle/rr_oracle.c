@@ -263,6 +263,118 @@ int oracle_cemaneigegr4j(const double *prec, const double *mean_temp, const doub
 }
 
 /* ------------------------------------------------------------------------- */
+/* Cemaneige with SWE-SCA hysteresis: rrmpg/models/cemaneigehyst_model.py:5-166 */
+/* params (first four fields of the Hyst records) = CTG, Kf, Thacc, Rsp          */
+/* numba lowers max(a,b) to (b > a) ? b : a and min(a,b) to (b < a) ? b : a.     */
+/* Quirk kept: at t = 0 the accumulation branch reads sca[t-1] = sca[T-1], which */
+/* still holds its np.zeros value (or sca_init itself when T == 1), :126.        */
+/* sca_o / G_o / eTG_o are [T,L,N]-style (stride ldg); rain_o [T,L] dense.       */
+/* ------------------------------------------------------------------------- */
+#define NB_MAX(a, b) (((b) > (a)) ? (b) : (a))
+void oracle_cemaneigehyst(const double *prec, const double *mean_temp, const double *frac,
+                          int64_t T, int64_t L, double snow_pack_init, double thermal_state_init,
+                          double sca_init, const double *p, double *lw, double *outflow, int64_t ld,
+                          double *G_o, double *eTG_o, double *sca_o, int64_t ldg, double *rain_o)
+{
+    const double CTG = p[0], Kf = p[1], Thacc = p[2], Rsp = p[3];
+    for (int64_t l = 0; l < L; ++l) {
+        double acc = 0.0;
+        for (int64_t t = 0; t < T; ++t) acc += prec[t * L + l] * frac[t * L + l];
+        const double Psolannual = 365.25 * (acc / (double)T);          /* :102 */
+        double G = 0.0, eTG = 0.0, swe_max = 0.0, Thmax = 0.0;
+        double sca_prev = (T == 1) ? sca_init : 0.0;                     /* sca[-1] at t = 0 */
+        for (int64_t t = 0; t < T; ++t) {
+            const double snow = prec[t * L + l] * frac[t * L + l];
+            const double rain = prec[t * L + l] - snow;                  /* :99 */
+            const double Tm = mean_temp[t * L + l];
+            double sca;
+            if (t == 0) { G = snow_pack_init; sca = sca_init; }          /* :107-109 */
+            else G = G + snow;                                           /* :111 */
+            if (t == 0) eTG = thermal_state_init;                        /* :114-115 */
+            else eTG = CTG * eTG + (1 - CTG) * Tm;                       /* :117 */
+            if (eTG > 0) eTG = 0.0;                                      /* :118-119 */
+            double pot_melt;
+            if (eTG == 0 && Tm > 0) {                                    /* :122 */
+                pot_melt = Kf * Tm;
+                if (pot_melt > G) pot_melt = G;
+            } else pot_melt = 0.0;
+            const double snow_balance = snow - pot_melt;                 /* :131 */
+            if (snow_balance >= 0) {                                     /* :133 */
+                sca = sca_prev + snow_balance / Thacc;                   /* :135 */
+                swe_max = NB_MAX(swe_max, G);                            /* :136 */
+            } else {
+                const double Thmelt = Psolannual * Rsp;                  /* :139 */
+                if (swe_max > Thmelt) Thmax = Thmelt;                    /* :142-145 */
+                else Thmax = swe_max;
+                if (Thmax > 0) sca = G / Thmax;                          /* :148-151 */
+                else sca = 0.0;
+            }
+            { const double m = NB_MAX(sca, 0.0); sca = NB_MIN(m, 1.0); } /* :154 */
+            double melt = (0.9 * sca + 0.1) * pot_melt;                  /* :157 */
+            melt = NB_MIN(melt, G);                                      /* :160 */
+            G = G - melt;                                                /* :163 */
+            if (G == 0) swe_max = 0.0;                                   /* :166-167 */
+            lw[t * L + l] = rain + melt;                                 /* :171 */
+            if (G_o) { G_o[(t * L + l) * ldg] = G; eTG_o[(t * L + l) * ldg] = eTG; sca_o[(t * L + l) * ldg] = sca; }
+            if (rain_o) rain_o[t * L + l] = rain;
+            sca_prev = sca;
+        }
+    }
+    (void)NB_MAX(0.0, 0.0);
+    for (int64_t t = 0; t < T; ++t) {
+        double acc = 0.0;
+        for (int64_t l = 0; l < L; ++l) acc += lw[t * L + l];
+        outflow[t * ld] = acc / (double)L;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Snow + ice + GR4J couplings:                                                */
+/*   run_cemaneigegr4jice       rrmpg/models/cemaneigegr4jice_model.py:16-93    */
+/*   run_cemaneigehystgr4j      rrmpg/models/cemaneigehystgr4j_model.py:17-79   */
+/*   run_cemaneigehystgr4jice   rrmpg/models/cemaneigehystgr4jice_model.py:18-104 */
+/*   run_icemelt                rrmpg/models/icemelt_model.py:16-65             */
+/* One restatement with two switches.  Record layouts:                          */
+/*   !hyst, ice : CTG Kf x1 x2 x3 x4 DDF          hyst, !ice: CTG Kf Thacc Rsp x1..x4 */
+/*    hyst, ice : CTG Kf Thacc Rsp x1 x2 x3 x4 DDF                                 */
+/* scratch: lw [T,L], Gs [T,L] (final snow pack per step), es [T,L], liq [T], snowmelt [T] */
+/* ------------------------------------------------------------------------- */
+int oracle_snowice_gr4j(int hyst, int ice, const double *prec, const double *mean_temp,
+                        const double *etp, const double *frac_ice, const double *frac, int64_t T,
+                        int64_t L, const double *inits /* g0,e0,sca0,s,r */, const double *p,
+                        double *scratch, double *qsim, int64_t ld, double *G_o, double *eTG_o,
+                        double *sca_o, int64_t ldg, double *s_o, double *r_o, double *icemelt_o,
+                        double *snowmelt_o, double *rain_o)
+{
+    double *lw = scratch, *Gs = lw + T * L, *es = Gs + T * L, *ss = es + T * L;
+    double *liq = ss + T * L, *sm = liq + T;
+    if (hyst) oracle_cemaneigehyst(prec, mean_temp, frac, T, L, inits[0], inits[1], inits[2], p, lw, sm, 1,
+                                   Gs, es, ss, 1, rain_o);
+    else oracle_cemaneige(prec, mean_temp, frac, T, L, inits[0], inits[1], p, lw, sm, 1, Gs, es, 1);
+    const int goff = hyst ? 4 : 2;
+    for (int64_t t = 0; t < T; ++t) {
+        double total = 0.0;
+        if (ice) {
+            const double ddf = p[goff + 4];
+            for (int64_t l = 0; l < L; ++l) {                        /* icemelt_model.py:52-62 */
+                double melt = ddf * (mean_temp[t * L + l] - 0);
+                if (melt < 0) melt = 0.0;
+                const double w = (Gs[t * L + l] > 1) ? 0.0 : melt;
+                total += w * frac_ice[l];                            /* np.sum(icemelt * frac_ice, axis=1) */
+            }
+            liq[t] = sm[t] + total;                                  /* cemaneigegr4jice_model.py:87 */
+        } else liq[t] = sm[t];
+        if (icemelt_o) icemelt_o[t * ld] = total;
+        if (snowmelt_o) snowmelt_o[t * ld] = sm[t];
+        if (G_o) for (int64_t l = 0; l < L; ++l) {
+            G_o[(t * L + l) * ldg] = Gs[t * L + l]; eTG_o[(t * L + l) * ldg] = es[t * L + l];
+            if (sca_o) sca_o[(t * L + l) * ldg] = hyst ? ss[t * L + l] : 0.0;
+        }
+    }
+    return oracle_gr4j(liq, etp, T, inits[3], inits[4], p + goff, qsim, ld, s_o, r_o);
+}
+
+/* ------------------------------------------------------------------------- */
 /* Forcing preprocessors: rrmpg/models/cemaneige_utils.py                     */
 /* ------------------------------------------------------------------------- */
 /* extrapolate_precipitation :101-158 */
@@ -541,6 +653,41 @@ int oracle_cemaneigegr4j_batch(const double *prec, const double *mean_temp, cons
     c.a0 = prec; c.a1 = mean_temp; c.a2 = frac; c.a3 = etp; c.T = T; c.L = L; c.N = N;
     c.inits = inits; c.params = params; c.o0 = qsim; c.o1 = G_o; c.o2 = eTG_o; c.o3 = s_o; c.o4 = r_o;
     parallel_members(N, nthreads, cg_span, &c);
+    return c.rc;
+}
+
+typedef struct {
+    int hyst, ice; const double *prec, *mt, *etp, *fice, *frac; int64_t T, L, N, k; const double *inits, *params;
+    double *q, *G, *E, *S, *s, *r, *im, *smelt; int rc;
+} sictx_t;
+static void snowice_span(int64_t lo, int64_t hi, void *v)
+{
+    sictx_t *c = (sictx_t *)v;
+    const int64_t T = c->T, L = c->L, TL = T * L;
+    double *scratch = (double *)malloc(sizeof(double) * (size_t)(4 * TL + 2 * T + 8));
+    for (int64_t i = lo; i < hi; ++i) {
+        int rc = oracle_snowice_gr4j(c->hyst, c->ice, c->prec, c->mt, c->etp, c->fice, c->frac, T, L, c->inits,
+                                     c->params + c->k * i, scratch, c->q + i, c->N,
+                                     c->G ? c->G + i : NULL, c->E ? c->E + i : NULL,
+                                     c->S ? c->S + i : NULL, c->N, c->s ? c->s + i : NULL,
+                                     c->r ? c->r + i : NULL, c->im ? c->im + i : NULL,
+                                     c->smelt ? c->smelt + i : NULL, NULL);
+        if (rc) __atomic_store_n(&c->rc, rc, __ATOMIC_RELAXED);
+    }
+    free(scratch);
+}
+/* member loops of cemaneigegr4jice.py:262-284, cemaneigehystgr4j.py:262-286, cemaneigehystgr4jice.py:276-304 */
+int oracle_snowice_gr4j_batch(int hyst, int ice, const double *prec, const double *mean_temp, const double *etp,
+                              const double *frac_ice, const double *frac, int64_t T, int64_t L,
+                              const double *inits, const double *params, int64_t N, double *qsim, double *G_o,
+                              double *eTG_o, double *sca_o, double *s_o, double *r_o, double *icemelt_o,
+                              double *snowmelt_o, int nthreads)
+{
+    sictx_t c; memset(&c, 0, sizeof(c));
+    c.hyst = hyst; c.ice = ice; c.prec = prec; c.mt = mean_temp; c.etp = etp; c.fice = frac_ice; c.frac = frac;
+    c.T = T; c.L = L; c.N = N; c.k = 6 + (hyst ? 2 : 0) + (ice ? 1 : 0); c.inits = inits; c.params = params;
+    c.q = qsim; c.G = G_o; c.E = eTG_o; c.S = sca_o; c.s = s_o; c.r = r_o; c.im = icemelt_o; c.smelt = snowmelt_o;
+    parallel_members(N, nthreads, snowice_span, &c);
     return c.rc;
 }
 

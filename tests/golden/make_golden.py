@@ -27,7 +27,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
-from rrmpg.models import ABCModel, HBVEdu, GR4J, Cemaneige, CemaneigeGR4J  # noqa: E402
+from rrmpg.models import (ABCModel, HBVEdu, GR4J, Cemaneige, CemaneigeGR4J, CemaneigeGR4JIce,  # noqa: E402
+                          CemaneigeHystGR4J, CemaneigeHystGR4JIce)
 from rrmpg.models.abcmodel_model import run_abcmodel  # noqa: E402
 from rrmpg.models.hbvedu_model import run_hbvedu  # noqa: E402
 from rrmpg.models.gr4j_model import run_gr4j  # noqa: E402
@@ -365,10 +366,124 @@ def ensembles():
     save("ensemble_hbvedu_mse", qobs=qobs, mse=mse)
 
 
+# --------------------------------------------------------------------------------------
+# 3. snow-ice family: CemaneigeGR4JIce, CemaneigeHystGR4J, CemaneigeHystGR4JIce
+# --------------------------------------------------------------------------------------
+SI_NAMES = ["qsim", "G", "eTG", "s_store", "r_store", "sca", "icemelt", "snowmelt", "rain"]
+
+
+def si_reference(model, hyst, ice, kw, frac_ice):
+    """Run the reference wrapper with return_storages=True and map its tuple onto SI_NAMES."""
+    if ice:
+        out = model.simulate(kw["prec"], kw["mean_temp"], kw["min_temp"], kw["max_temp"], kw["etp"], frac_ice,
+                             **kw["rest"], return_storages=True)
+    else:
+        out = model.simulate(kw["prec"], kw["mean_temp"], kw["min_temp"], kw["max_temp"], kw["etp"],
+                             **kw["rest"], return_storages=True)
+    d = {}
+    if hyst and ice:      # cemaneigehystgr4jice.py:304
+        keys = ["qsim", "G", "eTG", "s_store", "r_store", "sca", "icemelt", "snowmelt", "rain"]
+    elif hyst:            # cemaneigehystgr4j.py:288
+        keys = ["qsim", "G", "eTG", "s_store", "r_store", "sca", "rain"]
+    else:                 # cemaneigegr4jice.py:286
+        keys = ["qsim", "G", "eTG", "s_store", "r_store", "icemelt"]
+    for k, a in zip(keys, out):
+        d[k] = a
+    return d
+
+
+def si_case(tag, model, hyst, ice, raw, etp, station, alts, frac_ice, inits5, params, extra=None):
+    """inits5 = (snow_pack_init, thermal_state_init, sca_init, s_init, r_init)."""
+    rest = dict(met_station_height=station, altitudes=list(alts), snow_pack_init=inits5[0],
+                thermal_state_init=inits5[1], s_init=inits5[3], r_init=inits5[4], params=params)
+    if hyst:
+        rest["sca_init"] = inits5[2]
+    ref = si_reference(model, hyst, ice, dict(prec=raw[0], mean_temp=raw[1], min_temp=raw[2], max_temp=raw[3],
+                                              etp=etp, rest=rest), frac_ice)
+    p, me, mn, mx, frac, _ = prep_layers(*raw, station, alts)
+    got = dict(zip(SI_NAMES, oracle.snowice_gr4j(hyst, ice, p, me, etp, frac_ice, frac, inits5, pack(params),
+                                                 return_storages=True)))
+    for k, a in ref.items():
+        b = got[k]
+        if k == "rain":
+            b = np.repeat(b[:, :, None], a.shape[2], axis=2)
+        pin(f"{tag}.{k}", a, b)
+    arrays = dict(prec=raw[0], mean_temp=raw[1], min_temp=raw[2], max_temp=raw[3], etp=etp,
+                  met_station_height=np.array(float(station)), altitudes=np.array(alts, float),
+                  frac_ice=np.array(frac_ice if frac_ice is not None else [], float), inits=np.array(inits5, float),
+                  params=pack(params))
+    for k, a in ref.items():
+        if k == "rain":
+            a = a[:, :, 0]
+        arrays[k] = a
+    if extra:
+        arrays.update(extra)
+    save(tag, **arrays)
+
+
+def snow_ice_family():
+    alts = [550, 620, 700, 785, 920]
+    # ---- reference fixtures (test/test_models.py:270-356)
+    df = pd.read_csv(f"{DATA}/cemaneigehystgr4j_validation_data.csv", index_col=0)
+    pd_ = {"Thacc": 18.6, "Rsp": 0.22, "CTG": 0.78, "Kf": 4.02, "x1": 546, "x2": 0.53, "x3": 276, "x4": 1.32}
+    m = CemaneigeHystGR4J(params=pd_)
+    q = m.simulate(df.precipitation, df.mean_temp, df.min_temp, df.max_temp, df.pe, met_station_height=700,
+                   altitudes=alts, s_init=0.5, r_init=0.4)
+    assert np.allclose(q.flatten(), df.qsim.to_numpy())
+    raw = [df[c].to_numpy(float) for c in ("precipitation", "mean_temp", "min_temp", "max_temp")]
+    P = np.zeros(1, m.get_dtype())
+    for k in m.get_parameter_names():
+        P[k] = pd_[k]
+    si_case("fixture_cemaneigehystgr4j", m, 1, 0, raw, df.pe.to_numpy(float), 700, alts, None,
+            (0.0, 0.0, 0.0, 0.5, 0.4), P, extra=dict(expected=df.qsim.to_numpy(float)))
+
+    df = pd.read_csv(f"{DATA}/cemaneigehystgr4jice_validation_data.csv", index_col=0)
+    pd_ = dict(pd_, DDF=5)
+    m = CemaneigeHystGR4JIce(params=pd_)
+    frac_ice = np.array([0.02, 0.04, 0.25, 0.51, 0.71])
+    q = m.simulate(df.precipitation, df.mean_temp, df.min_temp, df.max_temp, df.pe, frac_ice, met_station_height=700,
+                   altitudes=alts, s_init=0.5, r_init=0.4, sca_init=0.2)
+    assert np.allclose(q.flatten(), df.qsim.to_numpy())
+    raw = [df[c].to_numpy(float) for c in ("precipitation", "mean_temp", "min_temp", "max_temp")]
+    P = np.zeros(1, m.get_dtype())
+    for k in m.get_parameter_names():
+        P[k] = pd_[k]
+    si_case("fixture_cemaneigehystgr4jice", m, 1, 1, raw, df.pe.to_numpy(float), 700, alts, frac_ice,
+            (0.0, 0.0, 0.2, 0.5, 0.4), P, extra=dict(expected=df.qsim.to_numpy(float)))
+
+    # ---- seeded ensembles on the synthetic catchment (shifted colder so that ice and hysteresis are active)
+    T = 1096
+    f = synthetic.forcing(T)
+    raw = (f["prec"], f["temp"] - 3, f["min_temp"] - 3, f["max_temp"] - 3)
+    fice = np.array([0.0, 0.05, 0.2, 0.5, 0.8])
+    m = CemaneigeGR4JIce()
+    P = with_edges(synthetic.random_params(m, 12), [dict(DDF=1.0, x4=2.0), dict(DDF=30.0, Kf=1.0)])
+    si_case("ensemble_cemaneigegr4jice", m, 0, 1, raw, f["etp"], synthetic.MET_STATION_HEIGHT, alts, fice,
+            (8.0, -0.5, 0.0, 0.6, 0.7), P)
+    m = CemaneigeHystGR4J()
+    P = with_edges(synthetic.random_params(m, 12), [dict(Thacc=1.0, Rsp=0.0), dict(Thacc=1000.0, Rsp=1.0, x4=10.0),
+                                                    dict(x4=4.2, x1=10.0, x3=5000.0)])
+    si_case("ensemble_cemaneigehystgr4j", m, 1, 0, raw, f["etp"], synthetic.MET_STATION_HEIGHT, alts, None,
+            (5.0, 0.0, 0.3, 0.6, 0.7), P)
+    m = CemaneigeHystGR4JIce()
+    P = with_edges(synthetic.random_params(m, 12), [dict(DDF=0.0), dict(Thacc=5.0, Rsp=0.5, DDF=30.0, x4=6.5)])
+    si_case("ensemble_cemaneigehystgr4jice", m, 1, 1, raw, f["etp"], synthetic.MET_STATION_HEIGHT, alts, fice,
+            (0.0, 0.0, 0.0, 0.5, 0.4), P)
+    # single layer (no altitudes) + one-step series (the sca[t-1] wrap-around quirk at T == 1)
+    m = CemaneigeHystGR4JIce()
+    P = synthetic.random_params(m, 6)
+    si_case("ensemble_cemaneigehystgr4jice_L1", m, 1, 1, raw, f["etp"], 1800, [], np.array([0.4]),
+            (3.0, -1.0, 0.7, 0.5, 0.4), P)
+    raw1 = tuple(a[:1].copy() for a in raw)
+    si_case("ensemble_cemaneigehystgr4jice_T1", m, 1, 1, raw1, f["etp"][:1].copy(), 1800, [], np.array([0.4]),
+            (3.0, -1.0, 0.7, 0.5, 0.4), P)
+
+
 if __name__ == "__main__":
     oracle.build(force=True)
     fixture_hbvedu(); fixture_gr4j(); fixture_cemaneige(); fixture_cemaneigegr4j()
     ensembles()
+    snow_ice_family()
     n_ok = sum(ok for _, ok, _ in REPORT)
     print(f"\noracle pinned bit-for-bit against numba on {n_ok}/{len(REPORT)} arrays")
     with open(os.path.join(OUT, "PINNING.txt"), "w") as fh:
