@@ -157,6 +157,39 @@ RRB_API int rrb_cemaneigegr4j_simulate(const double* prec, const double* mean_te
                                const double* params, int64_t N, double* qsim, double* G, double* eTG,
                                double* s_store, double* r_store /* nullable x4 */, const rrb_opts* opts);
 
+/* ---- snow-ice family ----------------------------------------
+ * Same layer arrays as rrb_cemaneigegr4j_simulate.  frac_ice: [L] glaciated fraction per layer.
+ * inits (always host memory) = (snow_pack_init, thermal_state_init, s_init, r_init) for the model without
+ * hysteresis and (snow_pack_init, thermal_state_init, sca_init, s_init, r_init) for the two Hyst models.
+ * Storage outputs: pass all of a model's storages or none.  G, eTG, sca: [T, L, N]; the others [T, N].
+ * The member-independent `rain` array the Hyst wrappers also return (cemaneigehyst_model.py:98-99) is
+ * prec - prec * frac_solid and is formed by the host layer. */
+
+/* CemaneigeGR4JIce: run_cemaneigegr4jice rrmpg/models/cemaneigegr4jice_model.py:16, member loop
+ * cemaneigegr4jice.py:262-284.  params[N][7] = (CTG, Kf, x1, x2, x3, x4, DDF). */
+RRB_API int rrb_cemaneigegr4jice_simulate(const double* prec, const double* mean_temp, const double* etp,
+                                          const double* frac_ice, const double* frac_solid, int64_t T, int64_t L,
+                                          const double* inits, const double* params, int64_t N, double* qsim,
+                                          double* G, double* eTG, double* s_store, double* r_store,
+                                          double* icemelt /* nullable x5 */, const rrb_opts* opts);
+
+/* CemaneigeHystGR4J: run_cemaneigehystgr4j rrmpg/models/cemaneigehystgr4j_model.py:17, member loop
+ * cemaneigehystgr4j.py:262-286.  params[N][8] = (CTG, Kf, Thacc, Rsp, x1, x2, x3, x4). */
+RRB_API int rrb_cemaneigehystgr4j_simulate(const double* prec, const double* mean_temp, const double* etp,
+                                           const double* frac_solid, int64_t T, int64_t L, const double* inits,
+                                           const double* params, int64_t N, double* qsim, double* G, double* eTG,
+                                           double* s_store, double* r_store, double* sca /* nullable x5 */,
+                                           const rrb_opts* opts);
+
+/* CemaneigeHystGR4JIce: run_cemaneigehystgr4jice rrmpg/models/cemaneigehystgr4jice_model.py:18, member loop
+ * cemaneigehystgr4jice.py:276-304.  params[N][9] = (CTG, Kf, Thacc, Rsp, x1, x2, x3, x4, DDF). */
+RRB_API int rrb_cemaneigehystgr4jice_simulate(const double* prec, const double* mean_temp, const double* etp,
+                                              const double* frac_ice, const double* frac_solid, int64_t T, int64_t L,
+                                              const double* inits, const double* params, int64_t N, double* qsim,
+                                              double* G, double* eTG, double* s_store, double* r_store, double* sca,
+                                              double* icemelt, double* snowmelt /* nullable x7 */,
+                                              const rrb_opts* opts);
+
 /* ---- host-side checks of the FAST math (no GPU needed; used by the CPU test-suite) ------- */
 RRB_API void rrb_host_fast_pow(const double* x, const double* y, int64_t n, double* out);
 RRB_API void rrb_host_fast_exp2m1(const double* z, int64_t n, double* out);

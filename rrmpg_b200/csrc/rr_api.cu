@@ -100,8 +100,8 @@ enum BufSlot {
     B_QOBS,
     B_MSE,
     B_SCALAR,
-    B_OUT0,    // output ring: B_OUT0 + 2*k + slot, k < 5
-    B_COUNT = B_OUT0 + 10
+    B_OUT0,    // output ring: B_OUT0 + 2*k + slot, k < 8
+    B_COUNT = B_OUT0 + 16
 };
 
 struct Ctx {
@@ -721,7 +721,7 @@ int rrb_cemaneige_simulate(const double* prec, const double* mean_temp, const do
     const int LC = cema_layer_class((int)L);
     void *F, *gt;
     if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, cema_TT(LC)) * cema_R(LC), &F))) return rc;
-    if ((rc = P.c->ensure(B_GT, sizeof(double) * kCemaMaxLayers, &gt))) return rc;
+    if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers, &gt))) return rc;
     RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, nullptr, T, (int)L, (double*)F, (double*)gt, P.s));
     Job job;
     job.T = T; job.N = N;
@@ -767,7 +767,7 @@ int rrb_cemaneigegr4j_simulate(const double* prec, const double* mean_temp, cons
     const int LC = cema_layer_class((int)L);
     void *F, *gt;
     if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, cema_TT(LC)) * cema_R(LC), &F))) return rc;
-    if ((rc = P.c->ensure(B_GT, sizeof(double) * kCemaMaxLayers, &gt))) return rc;
+    if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers, &gt))) return rc;
     RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, d_etp, T, (int)L, (double*)F, (double*)gt, P.s));
     Job job;
     job.T = T; job.N = N;
@@ -781,6 +781,91 @@ int rrb_cemaneigegr4j_simulate(const double* prec, const double* mean_temp, cons
                                     out[2], out[3], out[4], sl, ob, cfg);
     };
     return run_job(*P.c, P.o, job, P.d_qobs, P.d_mse);
+}
+
+// ---- snow-ice family ----
+static int snowice_simulate(int family, const double* prec, const double* mean_temp, const double* etp,
+                            const double* frac_ice, const double* frac_solid, int64_t T, int64_t L, const double* inits,
+                            const double* params, int64_t N, const SnowIceOut& o, int n_storage_given,
+                            int n_storage_expected, const rrb_opts* opts) {
+    const bool hyst = family & 1, ice = family & 2;
+    const int k = 6 + (hyst ? 2 : 0) + (ice ? 1 : 0);
+    Prepared P;
+    int rc = prepare(opts, T, N, params, k, &P);
+    if (rc) return rc;
+    if (!prec || !mean_temp || !etp || !frac_solid || !inits || (ice && !frac_ice))
+        return fail(RRB_EINVAL, "NULL forcing / inits pointer");
+    if (L < 1) return fail(RRB_EINVAL, "L = %lld", (long long)L);
+    if (L > RRB_MAX_LAYERS) return fail(RRB_EUNSUPPORTED, "L = %lld elevation layers (max %d)", (long long)L, RRB_MAX_LAYERS);
+    if (n_storage_given != 0 && n_storage_given != n_storage_expected)
+        return fail(RRB_EINVAL, "pass all %d storage outputs of the model or none", n_storage_expected);
+    if (!o.qsim && !P.o.qobs && n_storage_given == 0) return fail(RRB_EINVAL, "nothing to compute");
+    if (N == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    const double *d_prec, *d_mt, *d_fr, *d_etp, *d_fice = nullptr;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(T * L), &d_prec))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(T * L), &d_mt))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW2, frac_solid, (size_t)(T * L), &d_fr))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW3, etp, (size_t)T, &d_etp))) return rc;
+    if (ice && (rc = stage_in(*P.c, P.o, B_RAW4, frac_ice, (size_t)L, &d_fice))) return rc;
+    if ((rc = stage_common(&P, T, N, params, k))) return rc;
+    // inits5 = (snow_pack_init, thermal_state_init, sca_init, s_init, r_init); host memory in both modes
+    double in5[5];
+    if (hyst) memcpy(in5, inits, sizeof(in5));
+    else { in5[0] = inits[0]; in5[1] = inits[1]; in5[2] = 0.0; in5[3] = inits[2]; in5[4] = inits[3]; }
+    double x4_max;
+    if ((rc = resolve_x4_max(&P, params, N, k, (hyst ? 4 : 2) + 3, &x4_max))) return rc;
+    if (!(x4_max <= RRB_MAX_X4))
+        return fail(RRB_EUNSUPPORTED, "GR4J x4 up to %g in this batch; the unit hydrograph buffers support x4 <= %g",
+                    x4_max, RRB_MAX_X4);
+    const int LC = cema_layer_class((int)L);
+    void *F, *gt;
+    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, cema_TT(LC)) * cema_R(LC), &F))) return rc;
+    if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers, &gt))) return rc;
+    RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, d_etp, T, (int)L, (double*)F, (double*)gt, P.s));
+    Job job;
+    job.T = T; job.N = N;
+    job.outs = {{o.qsim, N}, {o.G, L * N}, {o.eTG, L * N}, {o.s_store, N}, {o.r_store, N},
+                {o.sca, L * N}, {o.icemelt, N}, {o.snowmelt, N}};
+    job.state_slots = state_slots_snowice(family, (int)L, x4_max);
+    const double* dp = P.d_params;
+    const double i0 = in5[0], i1 = in5[1], i2 = in5[2], i3 = in5[3], i4 = in5[4];
+    job.launch = [=](const Slab& sl, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
+        const double in[5] = {i0, i1, i2, i3, i4};
+        SnowIceOut so{out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]};
+        return launch_snowice(family, (const double*)F, (const double*)gt, d_fice, T, (int)L, in, dp, N, x4_max, so, sl,
+                              ob, cfg);
+    };
+    return run_job(*P.c, P.o, job, P.d_qobs, P.d_mse);
+}
+
+int rrb_cemaneigegr4jice_simulate(const double* prec, const double* mean_temp, const double* etp, const double* frac_ice,
+                                  const double* frac_solid, int64_t T, int64_t L, const double* inits,
+                                  const double* params, int64_t N, double* qsim, double* G, double* eTG, double* s_store,
+                                  double* r_store, double* icemelt, const rrb_opts* opts) {
+    SnowIceOut o{qsim, G, eTG, s_store, r_store, nullptr, icemelt, nullptr};
+    const int n = (G != nullptr) + (eTG != nullptr) + (s_store != nullptr) + (r_store != nullptr) + (icemelt != nullptr);
+    return snowice_simulate(2, prec, mean_temp, etp, frac_ice, frac_solid, T, L, inits, params, N, o, n, 5, opts);
+}
+
+int rrb_cemaneigehystgr4j_simulate(const double* prec, const double* mean_temp, const double* etp,
+                                   const double* frac_solid, int64_t T, int64_t L, const double* inits,
+                                   const double* params, int64_t N, double* qsim, double* G, double* eTG,
+                                   double* s_store, double* r_store, double* sca, const rrb_opts* opts) {
+    SnowIceOut o{qsim, G, eTG, s_store, r_store, sca, nullptr, nullptr};
+    const int n = (G != nullptr) + (eTG != nullptr) + (s_store != nullptr) + (r_store != nullptr) + (sca != nullptr);
+    return snowice_simulate(1, prec, mean_temp, etp, nullptr, frac_solid, T, L, inits, params, N, o, n, 5, opts);
+}
+
+int rrb_cemaneigehystgr4jice_simulate(const double* prec, const double* mean_temp, const double* etp,
+                                      const double* frac_ice, const double* frac_solid, int64_t T, int64_t L,
+                                      const double* inits, const double* params, int64_t N, double* qsim, double* G,
+                                      double* eTG, double* s_store, double* r_store, double* sca, double* icemelt,
+                                      double* snowmelt, const rrb_opts* opts) {
+    SnowIceOut o{qsim, G, eTG, s_store, r_store, sca, icemelt, snowmelt};
+    const int n = (G != nullptr) + (eTG != nullptr) + (s_store != nullptr) + (r_store != nullptr) + (sca != nullptr) +
+                  (icemelt != nullptr) + (snowmelt != nullptr);
+    return snowice_simulate(3, prec, mean_temp, etp, frac_ice, frac_solid, T, L, inits, params, N, o, n, 7, opts);
 }
 
 // ---- host evaluation of the FAST math (CPU test-suite) ----

@@ -1,0 +1,343 @@
+// rr_cemaneige.cuh -- the Cemaneige-family ensemble kernel template, shared by rr_cemaneige.cu (Cemaneige,
+// CemaneigeGR4J) and rr_snowice.cu (CemaneigeGR4JIce, CemaneigeHystGR4J, CemaneigeHystGR4JIce).
+//
+// FAMILY bit 0 = SWE-SCA hysteresis snow routine (run_cemaneigehyst, rrmpg/models/cemaneigehyst_model.py:5-166)
+//        bit 1 = degree-day ice melt added to the snow-routine outflow (run_icemelt,
+//                rrmpg/models/icemelt_model.py:16-65; couplings cemaneigegr4jice_model.py:76-93,
+//                cemaneigehystgr4jice_model.py:89-104)
+// Everything outside GR4J is + - * / and compares, compiled without contraction: bit-identical to numba.
+#pragma once
+#include "rr_common.cuh"
+#include "rr_gr4j.cuh"
+#include "rr_kernels.h"
+
+namespace rrb {
+
+template <int LC>
+struct CemaGeom {
+    static constexpr int R = (3 * LC + 1 + 1) & ~1;
+    static constexpr int TT = kCemaTileDoubles / R;
+};
+
+struct NoGr4j {
+    static constexpr int kStateSlots = 0;
+};
+
+struct CemaOut {
+    double *q, *G, *eTG, *s_store, *r_store;
+    double *sca, *icemelt, *snowmelt;  // snow-ice family only
+};
+
+struct CemaArgs {
+    const double* F;
+    const double* g_tresh;   // [0, 16): G_tresh per layer; [16, 32): Psolannual per layer (hysteresis)
+    int L;
+    int64_t T;               // total series length
+    double g0, e0, sca0, s_init, r_init;
+    const double* params;
+    int64_t pstride;
+    int64_t N;
+    const double* frac_ice;  // device [L], ice models only
+};
+
+template <int LC>
+struct CemaF {  // forcing of one timestep: { snow[LC] | rain[LC] | mean_temp[LC] | etp | pad }
+    static constexpr int R = CemaGeom<LC>::R;
+    double v[R];
+    static __device__ __forceinline__ CemaF load(uint32_t addr) {
+        CemaF f;
+#pragma unroll
+        for (int k = 0; k < R; k += 2) {
+            const double2 a = lds_f64x2(addr + 8u * k);
+            f.v[k] = a.x;
+            f.v[k + 1] = a.y;
+        }
+        return f;
+    }
+};
+
+// numba's max(a, b) / min(a, b) on floats: (b > a) ? b : a and (b < a) ? b : a (probed against numba)
+__device__ __forceinline__ double nb_max(double a, double b) { return (b > a) ? b : a; }
+
+// PLAIN = discharge only (no storages, no fused objective): the output flags are compile-time constants
+// EXACT = the run has exactly LC layers (L == LC): the per-layer bound checks fold away
+template <int LC, class Gr4j, bool FAST, bool PLAIN, bool EXACT, int FAMILY>
+__global__ void cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
+    constexpr bool COUPLED = Gr4j::kStateSlots > 0;
+    constexpr bool HYST = (FAMILY & 1) != 0, ICE = (FAMILY & 2) != 0;
+    constexpr int R = CemaGeom<LC>::R, TT = CemaGeom<LC>::TT;
+    constexpr int GOFF = HYST ? 4 : 2;  // offset of x1 in the parameter record
+    const bool WRITEQ = PLAIN || out.q != nullptr, STORAGE = !PLAIN && out.G != nullptr,
+               OBJ = !PLAIN && obj.qobs != nullptr;  // CTA-uniform
+    const double* __restrict__ F = a.F;
+    const int64_t N = a.N;
+    int L = a.L;
+    const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // threads past the end of the ensemble recompute member N-1 and store the same values to the same
+    // addresses: no predicate lives in the time loop
+    const int64_t i = gi < N ? gi : N - 1;
+    const double* p = a.params + a.pstride * i;
+    // record = (CTG, Kf[, Thacc, Rsp][, x1, x2, x3, x4][, DDF]) -- cemaneige.py:64-65, cemaneigegr4j.py:67-72,
+    // cemaneigegr4jice.py:73-79, cemaneigehystgr4j.py:72-79, cemaneigehystgr4jice.py:78-86
+    const double CTG = p[0], Kf = p[1];
+    const double Thacc = HYST ? p[2] : 1.0, Rsp = HYST ? p[3] : 0.0;
+    const double DDF = ICE ? p[GOFF + 4] : 0.0;
+    double omCTG = 1 - CTG;  // loop invariant of cemaneige_model.py:94
+    pin(omCTG);
+    if (EXACT) L = LC;
+    double G[LC], eTG[LC], gt[LC], inv_gt[LC];
+    uint32_t gt_span[LC];
+    double sca_prev[HYST ? LC : 1], swe_max[HYST ? LC : 1], thmelt[HYST ? LC : 1], fice[ICE ? LC : 1];
+#pragma unroll
+    for (int l = 0; l < LC; ++l) {
+        G[l] = 0.0;
+        eTG[l] = 0.0;
+        gt[l] = (l < L) ? a.g_tresh[l] : 0.0;
+        inv_gt[l] = 1.0 / gt[l];
+        gt_span[l] = div_invariant_span(gt[l]);
+        if (HYST) {
+            // sca[t-1] at t = 0 is sca[T-1], still 0 from np.zeros -- or sca_init itself when T == 1 (:126)
+            sca_prev[l] = (a.T == 1) ? a.sca0 : 0.0;
+            swe_max[l] = 0.0;
+            thmelt[l] = ((l < L) ? a.g_tresh[kCemaMaxLayers + l] : 0.0) * Rsp;  // Psolannual * Rsp, :139
+        }
+        if (ICE) fice[l] = (l < L) ? a.frac_ice[l] : 0.0;
+    }
+    double inv_thacc = 1.0 / Thacc;
+    const uint32_t thacc_span = HYST ? div_invariant_span(Thacc) : 0u;
+    Gr4j gr;
+    if constexpr (COUPLED) gr.init(p + GOFF, a.s_init, a.r_init);
+    double acc = 0.0;
+    constexpr int kLayerSlots = HYST ? 4 : 2;
+    constexpr int kSlots = kLayerSlots * LC + Gr4j::kStateSlots;
+    if (slab.t_begin > 0) {
+#pragma unroll
+        for (int l = 0; l < LC; ++l) {
+            G[l] = slab.state[(int64_t)l * N + i];
+            eTG[l] = slab.state[(int64_t)(LC + l) * N + i];
+            if (HYST) {
+                sca_prev[l] = slab.state[(int64_t)(2 * LC + l) * N + i];
+                swe_max[l] = slab.state[(int64_t)(3 * LC + l) * N + i];
+            }
+        }
+        if constexpr (COUPLED) gr.load(slab.state + (int64_t)kLayerSlots * LC * N, N, i);
+        if (OBJ) acc = slab.state[(int64_t)kSlots * N + i];
+    }
+    int64_t stride = N, strideL = (int64_t)L * N;
+    pin(stride); pin(strideL);
+    const int64_t off = i + (slab.t_begin - slab.row0) * N;
+    const int64_t offL = i + (slab.t_begin - slab.row0) * L * N;  // [rows, L, N] storages
+    double* q_o = WRITEQ ? out.q + off : nullptr;
+    double* s_o = (COUPLED && STORAGE) ? out.s_store + off : nullptr;
+    double* r_o = (COUPLED && STORAGE) ? out.r_store + off : nullptr;
+    double* G_o = STORAGE ? out.G + offL : nullptr;
+    double* E_o = STORAGE ? out.eTG + offL : nullptr;
+    double* S_o = (HYST && STORAGE) ? out.sca + offL : nullptr;
+    double* im_o = (ICE && STORAGE) ? out.icemelt + off : nullptr;
+    double* sm_o = (FAMILY == 3 && STORAGE) ? out.snowmelt + off : nullptr;
+    const double layers = (double)L;
+    double inv_layers = 1.0 / layers;
+    pin(inv_layers);
+
+    extern __shared__ __align__(128) unsigned char rrb_smem[];
+    uint32_t tb = 0;
+    if (COUPLED && FAST) {
+        tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<R, TT>()));
+        pin(tb);
+    }
+
+    // one timestep; FIRST = the very first step of the series, where the stores take their initial values
+    // instead of being updated (cemaneige_model.py:85-92, cemaneigehyst_model.py:107-115)
+    auto step = [&](auto first_c, int64_t t, const double* f) {
+        constexpr bool FIRST = decltype(first_c)::value != 0;
+        double lw_sum = 0.0, ice_sum = 0.0;
+#pragma unroll
+        for (int l = 0; l < LC; ++l) {
+            if (EXACT || l < L) {
+                const double snow = f[l], rain = f[LC + l], Tm = f[2 * LC + l];
+                double g = FIRST ? a.g0 : G[l] + snow;                    // :85-88
+                double e = FIRST ? a.e0 : CTG * eTG[l] + omCTG * Tm;      // :91-94
+                e = (e > 0) ? 0.0 : e;                                    // :95-96
+                // potential melt (:99-106), branch-free
+                const double kt = Kf * Tm;
+                const double capped = (kt > g) ? g : kt;
+                const double pot = (e == 0 && Tm > 0) ? capped : 0.0;
+                double melt;
+                if constexpr (!HYST) {
+                    // snow-covered-area ratio (:109-112).  The division is only evaluated where it can change
+                    // the result: with pot == 0 and a non-negative pack the product (0.9 ratio + 0.1) * pot is
+                    // +0 for every ratio in [0, 1] (the sign-bit test over-approximates "G < 0": harmless).
+                    double ratio = 1.0;
+                    if (g < gt[l] && (pot != 0.0 || __double2hiint(g) < 0))
+                        ratio = div_by_invariant(g, gt[l], inv_gt[l], gt_span[l]);
+                    melt = (0.9 * ratio + 0.1) * pot;                     // :115
+                } else {
+                    // SWE-SCA hysteresis (cemaneigehyst_model.py:131-160)
+                    const double bal = snow - pot;                        // :131
+                    double sca;
+                    if (bal >= 0) {                                       // accumulation, :133-136
+                        sca = sca_prev[l] + div_by_invariant(bal, Thacc, inv_thacc, thacc_span);
+                        swe_max[l] = nb_max(swe_max[l], g);
+                    } else {                                              // ablation, :138-151
+                        const double thmax = (swe_max[l] > thmelt[l]) ? thmelt[l] : swe_max[l];
+                        sca = (thmax > 0) ? g / thmax : 0.0;
+                    }
+                    sca = nb_min(nb_max(sca, 0.0), 1.0);                  // :154
+                    melt = (0.9 * sca + 0.1) * pot;                       // :157
+                    melt = nb_min(melt, g);                               // :160
+                    sca_prev[l] = sca;
+                    if (STORAGE) st_stream(S_o + (int64_t)l * stride, sca);
+                }
+                g = g - melt;                                             // :118 / hyst :163
+                if (HYST && g == 0) swe_max[l] = 0.0;                     // hyst :166-167
+                lw_sum += rain + melt;                                    // :121, :125
+                if (ICE) {                                                // icemelt_model.py:52-62
+                    double im = DDF * Tm;                                 // temp - tbase, tbase = 0
+                    im = (im < 0) ? 0.0 : im;
+                    im = (g > 1) ? 0.0 : im;
+                    ice_sum += im * fice[l];                              // np.sum(icemelt * frac_ice, axis=1)
+                }
+                G[l] = g;
+                eTG[l] = e;
+                if (STORAGE) {
+                    st_stream(G_o + (int64_t)l * stride, g);
+                    st_stream(E_o + (int64_t)l * stride, e);
+                }
+            }
+        }
+        // np.mean over the layers (:124-125); x / 1 == x
+        const double snowmelt = (L == 1) ? lw_sum : div_by_invariant(lw_sum, layers, inv_layers, kDivSpanOk);
+        const double liquid = ICE ? snowmelt + ice_sum : snowmelt;        // cemaneigegr4jice_model.py:87
+        double qv = liquid;
+        if constexpr (COUPLED) qv = gr.step(liquid, f[3 * LC], tb);       // cemaneigegr4j_model.py:62
+        if (WRITEQ) {
+            st_stream(q_o, qv);
+            q_o += stride;
+        }
+        if (STORAGE) {
+            G_o += strideL;
+            E_o += strideL;
+            if (HYST) S_o += strideL;
+            if constexpr (COUPLED) {
+                st_stream(s_o, gr.S);
+                st_stream(r_o, gr.R);
+                s_o += stride;
+                r_o += stride;
+            }
+            if (ICE) {
+                st_stream(im_o, ice_sum);
+                im_o += stride;
+            }
+            if (FAMILY == 3) {
+                st_stream(sm_o, snowmelt);
+                sm_o += stride;
+            }
+        }
+        if (OBJ) {
+            const double d = obj.qobs[t] - qv;
+            acc += d * d;
+        }
+    };
+
+    int64_t t_first = slab.t_begin;
+    if (slab.t_begin == 0 && slab.t_end > 0) {  // t = 0 peeled: its forcing row comes straight from global memory
+        double f0[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) f0[k] = F[k];
+        step(ic<1>{}, 0, f0);
+        t_first = 1;
+    }
+    stream_forcing_grouped<R, TT, 1, CemaF<LC>>(F, t_first, slab.t_end, [&](auto, int64_t t, const CemaF<LC>* fp) {
+        step(ic<0>{}, t, fp[0].v);
+    });
+
+    if (gi < N) {
+        if (slab.save_state) {
+#pragma unroll
+            for (int l = 0; l < LC; ++l) {
+                slab.state[(int64_t)l * N + i] = G[l];
+                slab.state[(int64_t)(LC + l) * N + i] = eTG[l];
+                if (HYST) {
+                    slab.state[(int64_t)(2 * LC + l) * N + i] = sca_prev[l];
+                    slab.state[(int64_t)(3 * LC + l) * N + i] = swe_max[l];
+                }
+            }
+            if constexpr (COUPLED) gr.save(slab.state + (int64_t)kLayerSlots * LC * N, N, i);
+            if (OBJ) slab.state[(int64_t)kSlots * N + i] = acc;
+        }
+        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i] = acc / (double)obj.T;
+    }
+}
+
+inline int cema_uh_class(double x4_max) {
+    if (!(x4_max <= 64.0)) return -1;
+    if (x4_max <= 3.0) return 0;
+    if (x4_max <= 4.0) return 1;
+    if (x4_max <= 10.0) return 2;
+    return 3;
+}
+inline int cema_uh_slots(int c) {
+    switch (c) {
+        case 0: return 2 + 3 + 7;
+        case 1: return 2 + 4 + 9;
+        case 2: return 2 + 10 + 21;
+        default: return Gr4jMemberDyn::kStateSlots;
+    }
+}
+
+template <int LC, class Gr4j, bool FAST, int FAMILY>
+static cudaError_t cema_launch_variant(const CemaArgs& a, const CemaOut& out, const Slab& slab, const Objective& obj,
+                                       const LaunchCfg& cfg) {
+    constexpr int R = CemaGeom<LC>::R, TT = CemaGeom<LC>::TT;
+    const int block = cfg.block > 0 ? cfg.block : pick_block(a.N, cfg.sm_count, 128);
+    const unsigned grid = (unsigned)((a.N + block - 1) / block);
+    const size_t smem = forcing_smem_bytes<R, TT>() + ((FAST && Gr4j::kStateSlots > 0) ? fastmath_smem_bytes() : 0);
+    const bool plain = out.q && !out.G && !obj.qobs;
+#define RRB_CEMA(P_, E_) cema_kernel<LC, Gr4j, FAST, P_, E_, FAMILY><<<grid, block, smem, cfg.stream>>>(a, out, slab, obj)
+    if (FAMILY == 0) {
+        if (plain && a.L == LC) RRB_CEMA(true, true);
+        else if (a.L == LC) RRB_CEMA(false, true);
+        else RRB_CEMA(false, false);
+    } else {
+        RRB_CEMA(false, false);  // the snow-ice family keeps one general variant per configuration
+    }
+#undef RRB_CEMA
+    return cudaGetLastError();
+}
+
+template <int LC, int FAMILY>
+static cudaError_t cema_launch_coupled_lc(const CemaArgs& a, double x4_max, const CemaOut& out, const Slab& slab,
+                                          const Objective& obj, const LaunchCfg& cfg) {
+    const bool fast = cfg.math == RRB_MATH_FAST_;
+#define RRB_GO(M_, F_) return cema_launch_variant<LC, M_, F_, FAMILY>(a, out, slab, obj, cfg)
+    switch (cema_uh_class(x4_max)) {
+        case 0:
+            if (fast) RRB_GO(Gr4jUh3F, true);
+            RRB_GO(Gr4jUh3P, false);
+        case 1:
+            if (fast) RRB_GO(Gr4jUh4F, true);
+            RRB_GO(Gr4jUh4P, false);
+        case 2:
+            if (fast) RRB_GO(Gr4jUh10F, true);
+            RRB_GO(Gr4jUh10P, false);
+        case 3:
+            RRB_GO(Gr4jMemberDyn, false);
+        default:
+            return cudaErrorInvalidValue;
+    }
+#undef RRB_GO
+}
+
+template <int FAMILY>
+static cudaError_t cema_launch_coupled(const CemaArgs& a, double x4_max, const CemaOut& out, const Slab& slab,
+                                       const Objective& obj, const LaunchCfg& cfg) {
+    if (a.N <= 0) return cudaSuccess;
+    if (a.L < 1 || a.L > kCemaMaxLayers) return cudaErrorInvalidValue;
+    switch (cema_layer_class(a.L)) {
+        case 1: return cema_launch_coupled_lc<1, FAMILY>(a, x4_max, out, slab, obj, cfg);
+        case 5: return cema_launch_coupled_lc<5, FAMILY>(a, x4_max, out, slab, obj, cfg);
+        default: return cema_launch_coupled_lc<16, FAMILY>(a, x4_max, out, slab, obj, cfg);
+    }
+}
+
+}  // namespace rrb

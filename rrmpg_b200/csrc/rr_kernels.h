@@ -92,6 +92,16 @@ cudaError_t launch_cemaneigegr4j(const double* F, const double* g_tresh, int64_t
                                  double* eTG, double* s_store, double* r_store, const Slab& slab,
                                  const Objective& obj, const LaunchCfg& cfg);
 
+// snow-ice family: family bit 0 = hysteresis snow routine, bit 1 = ice melt.  inits5 = (snow_pack_init,
+// thermal_state_init, sca_init, s_init, r_init); outputs nullable (all storages of the family or none).
+struct SnowIceOut {
+    double *qsim, *G, *eTG, *s_store, *r_store, *sca, *icemelt, *snowmelt;
+};
+cudaError_t launch_snowice(int family, const double* F, const double* g_tresh, const double* frac_ice, int64_t T, int L,
+                           const double* inits5, const double* params, int64_t N, double x4_max, const SnowIceOut& o,
+                           const Slab& slab, const Objective& obj, const LaunchCfg& cfg);
+int state_slots_snowice(int family, int L, double x4_max);
+
 // number of carry slots a model needs in Slab::state
 int state_slots_abc();
 int state_slots_hbvedu();

@@ -196,6 +196,59 @@ def hbvedu(temp, prec, month0, PE_m, T_m, inits, params, return_storage=False, q
     return _result(c, ["qsim"] + names, [q] + st)
 
 
+def snowice_gr4j(hyst, ice, prec, mean_temp, etp, frac_ice, frac_solid, inits, params, return_storages=False,
+                 qobs=None, want_qsim=True, math=DEFAULT_MATH, device=None, block=0, slab_steps=0, out=None, x4_max=0.0):
+    """The snow(+hysteresis)(+ice)+GR4J couplings of the reference over an ensemble.
+
+    hyst=False, ice=True : CemaneigeGR4JIce     (run_cemaneigegr4jice, cemaneigegr4jice_model.py:16-93), 7 fields,
+                           inits = (snow_pack_init, thermal_state_init, s_init, r_init)
+    hyst=True,  ice=False: CemaneigeHystGR4J    (run_cemaneigehystgr4j, cemaneigehystgr4j_model.py:17-79), 8 fields
+    hyst=True,  ice=True : CemaneigeHystGR4JIce (run_cemaneigehystgr4jice, cemaneigehystgr4jice_model.py:18-104), 9
+                           inits = (snow_pack_init, thermal_state_init, sca_init, s_init, r_init) for both Hyst models
+    Result keys: qsim, G, eTG, s_store, r_store, then sca (hyst), icemelt (ice), snowmelt (hyst and ice).
+    """
+    if not (hyst or ice):
+        raise ValueError("use cemaneigegr4j for the plain coupling")
+    P0 = pack_params(params)
+    c = _Call([prec, mean_temp, etp, frac_solid, P0], math, device, block, slab_steps, qobs, x4_max)
+    prec = c.f64(prec); mean_temp = c.f64(mean_temp, prec.shape); frac_solid = c.f64(frac_solid, prec.shape)
+    etp = c.f64(etp); P = c.f64(P0)
+    inits = c.host_f64(inits, 5 if hyst else 4)
+    if prec.ndim != 2:
+        raise ValueError("layer arrays must be [T, L]")
+    (T, L), N = prec.shape, P.shape[0]
+    fice = c.f64(frac_ice, (L,)) if ice else None
+    if etp.shape[0] != T:
+        raise ValueError("etp must have the same length as the layer arrays")
+    k = 6 + (2 if hyst else 0) + (1 if ice else 0)
+    if P.shape[1] != k:
+        raise ValueError(f"parameter records of this model have {k} fields")
+    out = out or {}
+    st = return_storages
+    q = c.empty((T, N), out.get("qsim")) if want_qsim else None
+    G = c.empty((T, L, N), out.get("G")) if st else None
+    E = c.empty((T, L, N), out.get("eTG")) if st else None
+    s = c.empty((T, N), out.get("s_store")) if st else None
+    r = c.empty((T, N), out.get("r_store")) if st else None
+    sca = c.empty((T, L, N), out.get("sca")) if (st and hyst) else None
+    im = c.empty((T, N), out.get("icemelt")) if (st and ice) else None
+    sm = c.empty((T, N), out.get("snowmelt")) if (st and hyst and ice) else None
+    c.want_mse(N, T)
+    p_ = _lib.ptr
+    L_ = _lib.lib()
+    if hyst and ice:
+        _run(c, T, N, L_.rrb_cemaneigehystgr4jice_simulate, p_(prec), p_(mean_temp), p_(etp), p_(fice), p_(frac_solid),
+             T, L, p_(inits), p_(P), N, p_(q), p_(G), p_(E), p_(s), p_(r), p_(sca), p_(im), p_(sm), C.byref(c.opts))
+    elif hyst:
+        _run(c, T, N, L_.rrb_cemaneigehystgr4j_simulate, p_(prec), p_(mean_temp), p_(etp), p_(frac_solid), T, L,
+             p_(inits), p_(P), N, p_(q), p_(G), p_(E), p_(s), p_(r), p_(sca), C.byref(c.opts))
+    else:
+        _run(c, T, N, L_.rrb_cemaneigegr4jice_simulate, p_(prec), p_(mean_temp), p_(etp), p_(fice), p_(frac_solid), T, L,
+             p_(inits), p_(P), N, p_(q), p_(G), p_(E), p_(s), p_(r), p_(im), C.byref(c.opts))
+    return _result(c, ["qsim", "G", "eTG", "s_store", "r_store", "sca", "icemelt", "snowmelt"],
+                   [q, G, E, s, r, sca, im, sm])
+
+
 def hbvedu_multi(temp, prec, month0, PE_m, T_m, inits, params, return_storage=False, qobs=None, want_qsim=True,
                  math=DEFAULT_MATH, device=None, block=0, out=None):
     """HBV-Edu for C independent catchments with N members each, one launch.

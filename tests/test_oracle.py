@@ -111,3 +111,35 @@ def test_empty_and_single_step_series():
     assert q.shape == (1, 3) and (q == 0).all()
     q = oracle.gr4j(np.zeros(0), np.zeros(0), 0.5, 0.5, np.array([[300.0, 1.0, 50.0, 1.5]]))
     assert q.shape == (0, 1)
+
+
+SNOWICE = [("fixture_cemaneigehystgr4j", 1, 0), ("fixture_cemaneigehystgr4jice", 1, 1),
+           ("ensemble_cemaneigegr4jice", 0, 1), ("ensemble_cemaneigehystgr4j", 1, 0),
+           ("ensemble_cemaneigehystgr4jice", 1, 1), ("ensemble_cemaneigehystgr4jice_L1", 1, 1),
+           ("ensemble_cemaneigehystgr4jice_T1", 1, 1)]
+SI_NAMES = ["qsim", "G", "eTG", "s_store", "r_store", "sca", "icemelt", "snowmelt", "rain"]
+
+
+def snowice_layers(g):
+    alts = list(g["altitudes"]); h = float(g["met_station_height"])
+    if alts:
+        p = oracle.extrapolate_precipitation(g["prec"], alts, h)
+        mn, me, mx = oracle.extrapolate_temperature(g["min_temp"], g["mean_temp"], g["max_temp"], alts, h)
+    else:
+        alts = [h]
+        p, me, mn, mx = (g[k][:, None] for k in ("prec", "mean_temp", "min_temp", "max_temp"))
+    return p, me, oracle.calculate_solid_fraction(p, alts, me, mn, mx)
+
+
+def test_snow_ice_family_bit_exact_against_numba_and_fixtures():
+    import pytest
+    for name, hyst, ice in SNOWICE:
+        g = load_golden(name)
+        p, me, fr = snowice_layers(g)
+        out = dict(zip(SI_NAMES, oracle.snowice_gr4j(hyst, ice, p, me, g["etp"], g["frac_ice"] if ice else None, fr,
+                                                     g["inits"], g["params"], return_storages=True)))
+        for k in SI_NAMES:
+            if k in g:
+                assert_bits_equal(out[k], g[k], f"{name}.{k}")
+        if "expected" in g:  # test/test_models.py:270-356
+            assert np.allclose(out["qsim"].flatten(), g["expected"])

@@ -5,7 +5,8 @@ import pytest
 
 import oracle
 from rrmpg_b200 import engine, synthetic
-from rrmpg_b200.models import ABCModel, HBVEdu, GR4J, Cemaneige, CemaneigeGR4J
+from rrmpg_b200.models import (ABCModel, HBVEdu, GR4J, Cemaneige, CemaneigeGR4J, CemaneigeGR4JIce,
+                               CemaneigeHystGR4J, CemaneigeHystGR4JIce)
 from rrmpg_b200.tools import monte_carlo
 from conftest import assert_bits_equal, assert_close, load_golden
 
@@ -380,3 +381,63 @@ def test_empty_series_and_empty_ensembles():
     r = engine.hbvedu(np.zeros(5), np.zeros(5), np.zeros(5, np.int8), np.zeros(12), np.zeros(12), (0, 0, 0, 0),
                       np.zeros((0, 11)))
     assert r["qsim"].shape == (5, 0)
+
+
+# ------------------------------------------------------------------ snow-ice family
+SNOWICE = [("fixture_cemaneigehystgr4j", CemaneigeHystGR4J), ("fixture_cemaneigehystgr4jice", CemaneigeHystGR4JIce),
+           ("ensemble_cemaneigegr4jice", CemaneigeGR4JIce), ("ensemble_cemaneigehystgr4j", CemaneigeHystGR4J),
+           ("ensemble_cemaneigehystgr4jice", CemaneigeHystGR4JIce),
+           ("ensemble_cemaneigehystgr4jice_L1", CemaneigeHystGR4JIce),
+           ("ensemble_cemaneigehystgr4jice_T1", CemaneigeHystGR4JIce)]
+EXACT_KEYS = {"G", "eTG", "sca", "icemelt", "snowmelt", "rain"}  # no pow / tanh on these: bit-exact
+
+
+@pytest.mark.parametrize("name,cls", SNOWICE)
+@pytest.mark.parametrize("math", MATHS)
+def test_snow_ice_family_drop_ins(name, cls, math, monkeypatch):
+    monkeypatch.setattr(engine, "DEFAULT_MATH", math)
+    g = load_golden(name)
+    model = cls()
+    P = np.zeros(g["params"].shape[0], model.get_dtype())
+    for j, k in enumerate(model.get_dtype().names):
+        P[k] = g["params"][:, j]
+    ini = g["inits"]  # (snow_pack_init, thermal_state_init, sca_init, s_init, r_init)
+    kw = dict(met_station_height=float(g["met_station_height"]), altitudes=[float(a) for a in g["altitudes"]],
+              snow_pack_init=ini[0], thermal_state_init=ini[1], s_init=ini[3], r_init=ini[4], params=P,
+              return_storages=True)
+    args = [g["prec"], g["mean_temp"], g["min_temp"], g["max_temp"], g["etp"]]
+    if model._ice:
+        args.append(g["frac_ice"])
+    if model._hyst:
+        kw["sca_init"] = ini[2]
+    out = model.simulate(*args, **kw)
+    keys = ["qsim", "G", "eTG", "s_store", "r_store"] + (["sca"] if model._hyst else []) + \
+           (["icemelt"] if model._ice else []) + (["snowmelt"] if model._hyst and model._ice else []) + \
+           (["rain"] if model._hyst else [])
+    assert len(out) == len(keys)
+    for k, a in zip(keys, out):
+        ref = g[k]
+        if k == "rain":
+            ref = np.repeat(ref[:, :, None], P.size, axis=2)
+        if k in EXACT_KEYS:
+            assert_bits_equal(a, ref, f"{name}[{math}].{k}")
+        else:
+            assert_close(a, ref, f"{name}[{math}].{k}")
+    if "expected" in g:  # the reference's own criterion, test/test_models.py:270-356
+        assert np.allclose(out[0].flatten(), g["expected"])
+    kw["return_storages"] = False
+    assert_bits_equal(model.simulate(*args, **kw), out[0], "qsim-only call")
+
+
+def test_snow_ice_time_slabs_and_objective():
+    g = load_golden("ensemble_cemaneigehystgr4jice")
+    from test_oracle import snowice_layers
+    p, me, fr = snowice_layers(g)
+    args = (True, True, p, me, g["etp"], g["frac_ice"], fr, g["inits"], g["params"])
+    one = engine.snowice_gr4j(*args, return_storages=True, slab_steps=p.shape[0])
+    many = engine.snowice_gr4j(*args, return_storages=True, slab_steps=97)
+    for k in one:
+        assert_bits_equal(many[k], one[k], f"snow-ice slabs {k}")
+    qobs = synthetic.qobs_like(g["qsim"][:, 2])
+    r = engine.snowice_gr4j(*args, qobs=qobs, want_qsim=False, slab_steps=200)
+    np.testing.assert_allclose(r["mse"], oracle.mse_columns(qobs, g["qsim"]), rtol=1e-8)
