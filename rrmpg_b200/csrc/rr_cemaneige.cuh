@@ -144,6 +144,7 @@ __global__ void cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
     if (COUPLED && FAST) {
         tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<R, TT>()));
         pin(tb);
+        __syncthreads();  // the peeled first step below already reads the staged tables
     }
 
     // one timestep; FIRST = the very first step of the series, where the stores take their initial values

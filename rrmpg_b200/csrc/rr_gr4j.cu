@@ -68,7 +68,7 @@ __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double 
     uint32_t tb = 0;
     if (FAST) {
         tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<kGr4jR, kGr4jTT>()));
-        pin(tb);
+        pin(tb);  // first read happens after the __syncthreads() inside stream_forcing_grouped
     }
 
     stream_forcing_grouped<kGr4jR, kGr4jTT, kGr4jGroup, Gr4jF>(

@@ -441,3 +441,42 @@ def test_snow_ice_time_slabs_and_objective():
     qobs = synthetic.qobs_like(g["qsim"][:, 2])
     r = engine.snowice_gr4j(*args, qobs=qobs, want_qsim=False, slab_steps=200)
     np.testing.assert_allclose(r["mse"], oracle.mse_columns(qobs, g["qsim"]), rtol=1e-8)
+
+
+# ------------------------------------------------------------------ BASELINE configs 3 and 4 at (per-GPU) full size
+def test_full_size_gr4j_device_resident_properties():
+    """BASELINE config 3 shape, scaled to 2^18 members so the 30.6 GB result stays well inside HBM next to other
+    tenants' tests: device-mode run, sampled columns against the oracle, batch independence."""
+    import torch
+    T, N = synthetic.T_DAILY_40Y, 1 << 18
+    f = synthetic.forcing(T)
+    P = engine.pack_params(synthetic.random_params(GR4J(), N))
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    q = engine.gr4j(t(f["prec"]), t(f["etp"]), 0.6, 0.7, t(P), x4_max=float(P[:, 3].max()))["qsim"]
+    torch.cuda.synchronize()
+    assert q.shape == (T, N)
+    assert bool(torch.isfinite(q).all()) and bool((q >= 0).all())
+    idx = np.r_[0:32, N - 32:N, np.random.default_rng(1).integers(0, N, 64)]
+    ref = oracle.gr4j(f["prec"], f["etp"], 0.6, 0.7, P[idx])
+    assert_close(q[:, torch.as_tensor(idx, device=dev)].cpu().numpy(), ref, "gr4j 262k sampled columns")
+    del q
+    torch.cuda.empty_cache()
+
+
+def test_full_size_cemaneigegr4j_per_gpu_share():
+    """BASELINE config 4: 262 144 members over 8 GPUs = 32 768 per GPU, 40 years, 5 layers; host mode."""
+    T, N = synthetic.T_DAILY_40Y, 32768
+    f = synthetic.forcing(T)
+    P = synthetic.random_params(CemaneigeGR4J(), N)
+    q = CemaneigeGR4J().simulate(f["prec"], f["temp"], f["min_temp"], f["max_temp"], f["etp"],
+                                 met_station_height=synthetic.MET_STATION_HEIGHT, altitudes=synthetic.ALTITUDES,
+                                 s_init=0.6, r_init=0.7, params=P)
+    assert q.shape == (T, N) and np.isfinite(q).all()
+    idx = np.r_[0:16, N - 16:N, np.random.default_rng(2).integers(0, N, 32)]
+    alts = synthetic.ALTITUDES
+    p = oracle.extrapolate_precipitation(f["prec"], alts, synthetic.MET_STATION_HEIGHT)
+    mn, me, mx = oracle.extrapolate_temperature(f["min_temp"], f["temp"], f["max_temp"], alts, synthetic.MET_STATION_HEIGHT)
+    fr = oracle.calculate_solid_fraction(p, alts, me, mn, mx)
+    ref = oracle.cemaneigegr4j(p, me, f["etp"], fr, (0, 0, 0.6, 0.7), P[idx])
+    assert_close(q[:, idx], ref, "cemaneigegr4j 32k sampled columns")
