@@ -684,7 +684,7 @@ int rrb_gr4j_simulate(const double* prec, const double* etp, int64_t T, double s
         return fail(RRB_EUNSUPPORTED, "GR4J x4 up to %g in this batch; the unit hydrograph buffers support x4 <= %g",
                     x4_max, RRB_MAX_X4);
     void* F;
-    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, kGr4jTT) * kGr4jR, &F))) return rc;
+    if ((rc = P.c->ensure(B_F, forcing_bytes(T, kGr4jTT, kGr4jR), &F))) return rc;
     RRB_CUDA(pack_gr4j(d_prec, d_etp, T, (double*)F, P.s));
     Job job;
     job.T = T; job.N = N;
@@ -720,7 +720,7 @@ int rrb_cemaneige_simulate(const double* prec, const double* mean_temp, const do
     if ((rc = stage_common(&P, T, N, params, param_stride))) return rc;
     const int LC = cema_layer_class((int)L);
     void *F, *gt;
-    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, cema_TT(LC)) * cema_R(LC), &F))) return rc;
+    if ((rc = P.c->ensure(B_F, forcing_bytes(T, cema_TT(LC), cema_R(LC)), &F))) return rc;
     if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers, &gt))) return rc;
     RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, nullptr, T, (int)L, (double*)F, (double*)gt, P.s));
     Job job;
@@ -766,7 +766,7 @@ int rrb_cemaneigegr4j_simulate(const double* prec, const double* mean_temp, cons
                     x4_max, RRB_MAX_X4);
     const int LC = cema_layer_class((int)L);
     void *F, *gt;
-    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, cema_TT(LC)) * cema_R(LC), &F))) return rc;
+    if ((rc = P.c->ensure(B_F, forcing_bytes(T, cema_TT(LC), cema_R(LC)), &F))) return rc;
     if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers, &gt))) return rc;
     RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, d_etp, T, (int)L, (double*)F, (double*)gt, P.s));
     Job job;
@@ -820,7 +820,7 @@ static int snowice_simulate(int family, const double* prec, const double* mean_t
                     x4_max, RRB_MAX_X4);
     const int LC = cema_layer_class((int)L);
     void *F, *gt;
-    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, cema_TT(LC)) * cema_R(LC), &F))) return rc;
+    if ((rc = P.c->ensure(B_F, forcing_bytes(T, cema_TT(LC), cema_R(LC)), &F))) return rc;
     if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers, &gt))) return rc;
     RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, d_etp, T, (int)L, (double*)F, (double*)gt, P.s));
     Job job;

@@ -23,20 +23,27 @@ static int layer_class(int L) { return cema_layer_class(L); }
 
 __global__ void cema_pack_kernel(const double* __restrict__ prec, const double* __restrict__ mean_temp,
                                  const double* __restrict__ frac, const double* __restrict__ etp, int64_t T,
-                                 int64_t Tpad, int L, int LC, int R, double* __restrict__ F) {
+                                 int64_t Tpad, int L, int LC, int R, double* __restrict__ F,
+                                 uint32_t* __restrict__ fflag) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= Tpad) return;
     double* row = F + t * R;
     for (int k = 0; k < R; ++k) row[k] = 0.0;
     if (t < T) {
+        bool ok = true;
         for (int l = 0; l < L; ++l) {
             const double p = prec[t * L + l];
             const double snow = p * frac[t * L + l];  // cemaneige_model.py:76
             row[l] = snow;
             row[LC + l] = p - snow;                   // :77
             row[2 * LC + l] = mean_temp[t * L + l];
+            ok = ok && forcing_value_sane(snow) && forcing_value_sane(p - snow) && forcing_value_sane(row[2 * LC + l]);
         }
-        if (etp) row[3 * LC] = etp[t];
+        if (etp) {
+            row[3 * LC] = etp[t];
+            ok = ok && forcing_value_sane(etp[t]);
+        }
+        if (!ok) atomicOr(fflag, 1u);
     }
 }
 
@@ -58,7 +65,10 @@ cudaError_t pack_cemaneige(const double* prec, const double* mean_temp, const do
     const int LC = layer_class(L);
     const int R = cema_R(LC);
     const int64_t Tpad = padded_steps(T, cema_TT(LC));
-    cema_pack_kernel<<<(unsigned)((Tpad + 127) / 128), 128, 0, s>>>(prec, mean_temp, frac, etp, T, Tpad, L, LC, R, F);
+    uint32_t* fflag = forcing_flag(F, T, cema_TT(LC), R);
+    cudaError_t e = cudaMemsetAsync(fflag, 0, kForcingFlagBytes, s);
+    if (e != cudaSuccess) return e;
+    cema_pack_kernel<<<(unsigned)((Tpad + 127) / 128), 128, 0, s>>>(prec, mean_temp, frac, etp, T, Tpad, L, LC, R, F, fflag);
     cema_gtresh_kernel<<<1, 32, 0, s>>>(F, T, L, R, g_tresh);
     return cudaGetLastError();
 }
@@ -73,7 +83,8 @@ cudaError_t launch_cemaneige(const double* F, const double* g_tresh, int64_t T, 
                              double* eTG, const Slab& slab, const Objective& obj, const LaunchCfg& cfg) {
     if (N <= 0) return cudaSuccess;
     if (L < 1 || L > kCemaMaxLayers) return cudaErrorInvalidValue;
-    CemaArgs a{F, g_tresh, L, T, g0, e0, 0.0, 0.0, 0.0, params, pstride, N, nullptr};
+    CemaArgs a{F, g_tresh, L, T, g0, e0, 0.0, 0.0, 0.0, params, pstride, N, nullptr,
+               forcing_flag(F, T, cema_TT(layer_class(L)), cema_R(layer_class(L)))};
     CemaOut out{outflow, G, eTG, nullptr, nullptr, nullptr, nullptr, nullptr};
     switch (layer_class(L)) {
         case 1: return cema_launch_variant<1, NoGr4j, false, 0>(a, out, slab, obj, cfg);
@@ -86,7 +97,8 @@ cudaError_t launch_cemaneigegr4j(const double* F, const double* g_tresh, int64_t
                                  const double* params, int64_t N, double x4_max, double* qsim, double* G,
                                  double* eTG, double* s_store, double* r_store, const Slab& slab,
                                  const Objective& obj, const LaunchCfg& cfg) {
-    CemaArgs a{F, g_tresh, L, T, inits4[0], inits4[1], 0.0, inits4[2], inits4[3], params, 6, N, nullptr};
+    CemaArgs a{F, g_tresh, L, T, inits4[0], inits4[1], 0.0, inits4[2], inits4[3], params, 6, N, nullptr,
+               forcing_flag(F, T, cema_TT(layer_class(L)), cema_R(layer_class(L)))};
     CemaOut out{qsim, G, eTG, s_store, r_store, nullptr, nullptr, nullptr};
     return cema_launch_coupled<0>(a, x4_max, out, slab, obj, cfg);
 }

@@ -38,6 +38,7 @@ struct CemaArgs {
     int64_t pstride;
     int64_t N;
     const double* frac_ice;  // device [L], ice models only
+    const uint32_t* fflag;   // forcing sanity flag written by the packer (rr_kernels.h)
 };
 
 template <int LC>
@@ -141,15 +142,30 @@ __global__ void cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
 
     extern __shared__ __align__(128) unsigned char rrb_smem[];
     uint32_t tb = 0;
-    if (COUPLED && FAST) {
+    bool use_fast = false;
+    Exp2Regs ek{};
+    if constexpr (COUPLED && FAST) {
         tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<R, TT>()));
         pin(tb);
-        __syncthreads();  // the peeled first step below already reads the staged tables
+        // FAST path contract of Gr4jMember: finite, moderately ranged parameters, initial states and forcing --
+        // then the snow routine feeds GR4J finite water.  CTA-uniform; the barrier also publishes the tables
+        // (the peeled first step below already reads them).
+        bool sane = gr.sane && *a.fflag == 0u && fabs(a.g0) <= 1e6 && fabs(a.e0) <= 1e6 && fabs(a.sca0) <= 1e6;
+        for (int k = 0; k < (int)a.pstride; ++k) sane = sane && fabs(p[k]) <= 1e6;
+        if (ICE) {
+#pragma unroll
+            for (int l = 0; l < LC; ++l) sane = sane && fabs(fice[l]) <= 1e6;
+        }
+        use_fast = __syncthreads_and(sane) != 0;
+        if (use_fast) {
+            ek = load_exp2_regs(tb);
+            gr.enter_fast();
+        }
     }
 
     // one timestep; FIRST = the very first step of the series, where the stores take their initial values
     // instead of being updated (cemaneige_model.py:85-92, cemaneigehyst_model.py:107-115)
-    auto step = [&](auto first_c, int64_t t, const double* f) {
+    auto step = [&](auto first_c, auto fast_c, int64_t t, const double* f) {
         constexpr bool FIRST = decltype(first_c)::value != 0;
         double lw_sum = 0.0, ice_sum = 0.0;
 #pragma unroll
@@ -210,7 +226,9 @@ __global__ void cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
         const double snowmelt = (L == 1) ? lw_sum : div_by_invariant(lw_sum, layers, inv_layers, kDivSpanOk);
         const double liquid = ICE ? snowmelt + ice_sum : snowmelt;        // cemaneigegr4jice_model.py:87
         double qv = liquid;
-        if constexpr (COUPLED) qv = gr.step(liquid, f[3 * LC], tb);       // cemaneigegr4j_model.py:62
+        if constexpr (COUPLED) {                                          // cemaneigegr4j_model.py:62
+            qv = gr4j_step(fast_c, gr, liquid, f[3 * LC], tb, ek);
+        }
         if (WRITEQ) {
             st_stream(q_o, qv);
             q_o += stride;
@@ -240,17 +258,25 @@ __global__ void cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
         }
     };
 
-    int64_t t_first = slab.t_begin;
-    if (slab.t_begin == 0 && slab.t_end > 0) {  // t = 0 peeled: its forcing row comes straight from global memory
-        double f0[R];
+    auto run = [&](auto fast_c) {
+        int64_t t_first = slab.t_begin;
+        if (slab.t_begin == 0 && slab.t_end > 0) {  // t = 0 peeled: its forcing row comes straight from global memory
+            double f0[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) f0[k] = F[k];
-        step(ic<1>{}, 0, f0);
-        t_first = 1;
+            for (int k = 0; k < R; ++k) f0[k] = F[k];
+            step(ic<1>{}, fast_c, 0, f0);
+            t_first = 1;
+        }
+        stream_forcing_grouped<R, TT, 1, CemaF<LC>>(F, t_first, slab.t_end, [&](auto, int64_t t, const CemaF<LC>* fp) {
+            step(ic<0>{}, fast_c, t, fp[0].v);
+        });
+    };
+    if constexpr (COUPLED && FAST) {
+        if (use_fast) run(ic<1>{});
+        else run(ic<0>{});
+    } else {
+        run(ic<0>{});
     }
-    stream_forcing_grouped<R, TT, 1, CemaF<LC>>(F, t_first, slab.t_end, [&](auto, int64_t t, const CemaF<LC>* fp) {
-        step(ic<0>{}, t, fp[0].v);
-    });
 
     if (gi < N) {
         if (slab.save_state) {

@@ -359,6 +359,9 @@ __device__ __forceinline__ void pin(double& v) { asm volatile("" : "+d"(v)); }
 __device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void pin(int64_t& v) { asm volatile("" : "+l"(v)); }
 
+// forcing values the FAST paths accept (finite, |x| <= 1e6); everything else selects the reference-order step
+__device__ __forceinline__ bool forcing_value_sane(double x) { return fabs(x) <= 1e6; }
+
 // dynamic shared memory = [forcing ring | mbarriers | (FAST math tables)], rounded to 16 B
 template <int R, int TT>
 __host__ __device__ constexpr size_t forcing_smem_bytes() {

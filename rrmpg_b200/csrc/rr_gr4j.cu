@@ -11,20 +11,24 @@
 namespace rrb {
 
 __global__ void gr4j_pack_kernel(const double* __restrict__ prec, const double* __restrict__ etp, int64_t T,
-                                 int64_t Tpad, double* __restrict__ F) {
+                                 int64_t Tpad, double* __restrict__ F, uint32_t* __restrict__ fflag) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= Tpad) return;
     double2 v = make_double2(0.0, 0.0);
     if (t < T) {
         v.x = prec[t];
         v.y = etp[t];
+        if (!forcing_value_sane(v.x) || !forcing_value_sane(v.y)) atomicOr(fflag, 1u);
     }
     reinterpret_cast<double2*>(F)[t] = v;
 }
 
 cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* F, cudaStream_t s) {
     int64_t Tpad = padded_steps(T, kGr4jTT);
-    gr4j_pack_kernel<<<(unsigned)((Tpad + 255) / 256), 256, 0, s>>>(prec, etp, T, Tpad, F);
+    uint32_t* fflag = forcing_flag(F, T, kGr4jTT, kGr4jR);
+    cudaError_t e = cudaMemsetAsync(fflag, 0, kForcingFlagBytes, s);
+    if (e != cudaSuccess) return e;
+    gr4j_pack_kernel<<<(unsigned)((Tpad + 255) / 256), 256, 0, s>>>(prec, etp, T, Tpad, F, fflag);
     return cudaGetLastError();
 }
 
@@ -43,7 +47,7 @@ template <class Member, bool FAST, bool PLAIN>
 __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double r_init,
                             const double* __restrict__ params, int64_t N, double* __restrict__ qsim,
                             double* __restrict__ s_store, double* __restrict__ r_store, Slab slab,
-                            Objective obj) {
+                            Objective obj, const uint32_t* __restrict__ fflag) {
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     // threads past the end of the ensemble recompute member N-1 and store the same values to the same
     // addresses: no predicate lives in the time loop
@@ -66,33 +70,49 @@ __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double 
 
     extern __shared__ __align__(128) unsigned char rrb_smem[];
     uint32_t tb = 0;
-    if (FAST) {
+    bool use_fast = false;
+    Exp2Regs ek{};
+    if constexpr (FAST) {
         tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<kGr4jR, kGr4jTT>()));
-        pin(tb);  // first read happens after the __syncthreads() inside stream_forcing_grouped
+        pin(tb);
+        // CTA-uniform choice of the step (Gr4jMember: FAST path contract); the barrier also publishes the tables
+        use_fast = __syncthreads_and(m.sane && *fflag == 0u) != 0;
+        if (use_fast) {
+            ek = load_exp2_regs(tb);
+            m.enter_fast();
+        }
     }
 
-    stream_forcing_grouped<kGr4jR, kGr4jTT, kGr4jGroup, Gr4jF>(
-        F, slab.t_begin, slab.t_end, [&](auto gc, int64_t t0, const Gr4jF* f) {
-            constexpr int G = decltype(gc)::value;
+    auto run = [&](auto fast_c) {
+        stream_forcing_grouped<kGr4jR, kGr4jTT, kGr4jGroup, Gr4jF>(
+            F, slab.t_begin, slab.t_end, [&](auto gc, int64_t t0, const Gr4jF* f) {
+                constexpr int G = decltype(gc)::value;
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const double qv = m.step(f[g].prec, f[g].etp, tb);
-                if (WRITEQ) {
-                    st_stream(q_o, qv);
-                    q_o += stride;
+                for (int g = 0; g < G; ++g) {
+                    const double qv = gr4j_step(fast_c, m, f[g].prec, f[g].etp, tb, ek);
+                    if (WRITEQ) {
+                        st_stream(q_o, qv);
+                        q_o += stride;
+                    }
+                    if (STORAGE) {
+                        st_stream(s_o, m.S);
+                        st_stream(r_o, m.R);
+                        s_o += stride;
+                        r_o += stride;
+                    }
+                    if (OBJ) {
+                        const double d = obj.qobs[t0 + g] - qv;
+                        acc += d * d;
+                    }
                 }
-                if (STORAGE) {
-                    st_stream(s_o, m.S);
-                    st_stream(r_o, m.R);
-                    s_o += stride;
-                    r_o += stride;
-                }
-                if (OBJ) {
-                    const double d = obj.qobs[t0 + g] - qv;
-                    acc += d * d;
-                }
-            }
-        });
+            });
+    };
+    if constexpr (FAST) {
+        if (use_fast) run(ic<1>{});
+        else run(ic<0>{});
+    } else {
+        run(ic<0>{});
+    }
 
     if (gi < N) {
         if (slab.save_state) {
@@ -122,28 +142,28 @@ int state_slots_gr4j(double x4_max) {
 }
 
 template <class Member, bool FAST>
-static cudaError_t launch_variant(const double* F, double s_init, double r_init, const double* params, int64_t N,
+static cudaError_t launch_variant(const double* F, int64_t T, double s_init, double r_init, const double* params, int64_t N,
                                   double* qsim, double* s_store, double* r_store, const Slab& slab,
                                   const Objective& obj, const LaunchCfg& cfg) {
     const int block = cfg.block > 0 ? cfg.block : pick_block(N, cfg.sm_count, 128);
     const unsigned grid = (unsigned)((N + block - 1) / block);
     const size_t smem = forcing_smem_bytes<kGr4jR, kGr4jTT>() + (FAST ? fastmath_smem_bytes() : 0);
+    const uint32_t* fflag = forcing_flag(F, T, kGr4jTT, kGr4jR);
     if (qsim && !s_store && !obj.qobs)
         gr4j_kernel<Member, FAST, true><<<grid, block, smem, cfg.stream>>>(F, s_init, r_init, params, N, qsim, s_store,
-                                                                           r_store, slab, obj);
+                                                                           r_store, slab, obj, fflag);
     else
         gr4j_kernel<Member, FAST, false><<<grid, block, smem, cfg.stream>>>(F, s_init, r_init, params, N, qsim, s_store,
-                                                                            r_store, slab, obj);
+                                                                            r_store, slab, obj, fflag);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gr4j(const double* F, int64_t T, double s_init, double r_init, const double* params,
                         int64_t N, double x4_max, double* qsim, double* s_store, double* r_store,
                         const Slab& slab, const Objective& obj, const LaunchCfg& cfg) {
-    (void)T;
     if (N <= 0) return cudaSuccess;
     const bool fast = cfg.math == RRB_MATH_FAST_;
-#define RRB_GO(M_, F_) return launch_variant<M_, F_>(F, s_init, r_init, params, N, qsim, s_store, r_store, slab, obj, cfg)
+#define RRB_GO(M_, F_) return launch_variant<M_, F_>(F, T, s_init, r_init, params, N, qsim, s_store, r_store, slab, obj, cfg)
     switch (uh_class(x4_max)) {
         case 0:
             if (fast) RRB_GO(Gr4jUh3F, true);

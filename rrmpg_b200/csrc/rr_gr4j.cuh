@@ -43,6 +43,7 @@ struct Gr4jMember {
         k_tanh = 2.8853900817779268 / x1;  // 2 / ln 2
         k49 = (4.0 / 9.0) / x1;
         if (MATH == RRB_MATH_FAST_) { pin(inv_x1); pin(inv_x3); pin(k_tanh); pin(k49); }
+        judge(p, s_init, r_init);
         S = s_init * x1;  // :64
         R = r_init * x3;  // :65
         n1 = (int)ceil(x4);          // :68
@@ -78,9 +79,30 @@ struct Gr4jMember {
         for (int j = 0; j < C2; ++j) state[(2 + C1 + j) * N + i] = u2[j];
     }
 
+    // ---- FAST path contract -----------------------------------------------------------------------
+    // step_fast() carries no special-value handling: it is only entered when every member of the CTA is
+    // "sane" (finite parameters of moderate magnitude, finite initial states) and the packed forcing is
+    // finite and moderately ranged (flag written by the pack kernel).  Then every store stays finite
+    // (S <= 2.25 x1 + P and R <= x3 + UH water after each step), no operand can reach the ranges where the
+    // branch-free sequences of rr_math.cuh differ from libm, and NaN never appears.  Otherwise the CTA runs
+    // step_precise(): the reference's operations, special values included.
+    bool sane;
+    __device__ __forceinline__ void judge(const double* p, double s_init, double r_init) {
+        sane = p[0] >= 1e-3 && p[0] <= 1e6 && p[2] >= 1e-3 && p[2] <= 1e6 && fabs(p[1]) <= 1e4 && p[3] > 0.0 &&
+               p[3] <= 64.0 && fabs(s_init) <= 1e3 && fabs(r_init) <= 1e3;
+    }
+    // FAST folds the 0.9 / 0.1 split of the routed water (:126-127) into the unit hydrograph ordinates
+    __device__ __forceinline__ void enter_fast() {
+#pragma unroll
+        for (int j = 0; j < C1; ++j) o1[j] *= 0.9;
+#pragma unroll
+        for (int j = 0; j < C2; ++j) o2[j] *= 0.1;
+    }
+
     // one timestep: P = precipitation (or Cemaneige liquid outflow), E = potential evapotranspiration
-    __device__ __forceinline__ double step(double P, double E, uint32_t tb) {
-        if (MATH == RRB_MATH_FAST_) return step_fast(P, E, tb);
+    __device__ __forceinline__ double step(double P, double E, uint32_t) { return step_precise(P, E); }
+
+    __device__ __forceinline__ double step_precise(double P, double E) {
         const bool wet = P >= E;                   // :89
         const double arg = wet ? P - E : E - P;    // p_n (:90) or pe_n (:101)
         const double p_n = wet ? arg : 0.0;
@@ -122,50 +144,62 @@ struct Gr4jMember {
         return q_r + q_d;                        // :154
     }
 
-    // FAST: same recurrence, fewer fp64 instructions (every one of them costs two issue slots):
-    //  * tanh(a) = m/(m+2) with m = expm1(2a), so both production-store formulas collapse to
-    //    num*m / (2 + c*m) -- one table-driven expm1 and one branch-free division,
-    //  * reciprocals of x1 / x3 hoisted, (1+u^4)^(-1/4) and w^3.5 from the reciprocal-square-root unit,
-    //  * the unit hydrographs as one FMA per slot.  A padded slot holds 0 * p: identical to the reference
-    //    for finite p (sign of zero aside); a member whose routed water became inf reads NaN instead.
-    __device__ __forceinline__ double step_fast(double P, double E, uint32_t tb) {
-        const bool wet = P >= E;
-        const double arg = fabs(P - E);
+    // FAST (sane operands only, see above): same recurrence, ~80 fp64 instructions instead of ~107
+    // (every one of them costs two issue slots), one basic block:
+    //  * wet / dry through the sign of d = P - E (P >= E <=> d >= +0; d = -0 needs P = -0 and gives a zero
+    //    argument, for which both branches of the reference coincide),
+    //  * tanh(a) = m/(m+2) with m = expm1(2a): both production-store formulas collapse to
+    //    num m / (2 + c m) with num = base - S sr, base = x1 | 2S and c = 1 + sr | 2 - sr,
+    //  * reciprocals of x1 / x3 hoisted; (1+u^4)^(-1/4), w^3.5 and 1/den from the reciprocal / reciprocal
+    //    square root seed units with one third-order correction each,
+    //  * S (1 - y) as one FMA, the unit hydrographs as one FMA per slot on pre-scaled ordinates.  A padded
+    //    slot holds 0 * p = 0: identical to the reference for finite p.
+    __device__ __forceinline__ double step_fast(double P, double E, uint32_t tb, const Exp2Regs& k) {
+        const double d = P - E;
+        const int hd = __double2hiint(d);
+        const bool wet = hd >= 0;
+        const double arg = fabs(d);
         const double sr = S * inv_x1;
-        const double m = fast_exp2m1_nonneg_smem(arg * k_tanh, tb);
-        double num, c;
-        if (wet) {
-            num = x1 * fma(-sr, sr, 1.0);
-            c = 1.0 + sr;
-        } else {
-            num = S * (2.0 - sr);
-            c = 2.0 - sr;
-        }
-        const double frac = fast_div_pos(num * m, fma(c, m, 2.0));
-        const double dS = wet ? frac : -frac;   // + p_s or - e_s
-        S = S + dS;
+        const double m = exp2m1_sane(arg * k_tanh, tb, k);
+        const double sgn = __hiloint2double(0x3FF00000 | (hd & (int)0x80000000), 0);  // +1 wet, -1 dry
+        const double cbase = __hiloint2double(wet ? 0x3FF00000 : 0x40000000, 0);      // 1 wet, 2 dry
+        const double c = fma(sgn, sr, cbase);
+        const double base = wet ? x1 : S + S;
+        const double num = fma(-S, sr, base);
+        const double frac = (num * m) * rcp_sane(fma(c, m, 2.0));  // p_s (wet) or e_s (dry)
+        S = fma(sgn, frac, S);
         const double u = S * k49;
         const double uu = u * u;
-        const double perc = S * (1.0 - fast_rsqrt4_ge1(fma(uu, uu, 1.0)));
+        const double perc = fma(-S, rsqrt4_sane(fma(uu, uu, 1.0), k), S);
         S = S - perc;
-        const double p_r = wet ? perc + (arg - frac) : perc;
-        const double p1 = 0.9 * p_r;
-        const double p2 = 0.1 * p_r;
+        const double p_n = wet ? arg - frac : 0.0;
+        const double p_r = perc + p_n;
 #pragma unroll
-        for (int j = 0; j < C1 - 1; ++j) u1[j] = fma(o1[j], p1, u1[j + 1]);
-        u1[C1 - 1] = o1[C1 - 1] * p1;
+        for (int j = 0; j < C1 - 1; ++j) u1[j] = fma(o1[j], p_r, u1[j + 1]);
+        u1[C1 - 1] = o1[C1 - 1] * p_r;
 #pragma unroll
-        for (int j = 0; j < C2 - 1; ++j) u2[j] = fma(o2[j], p2, u2[j + 1]);
-        u2[C2 - 1] = o2[C2 - 1] * p2;
-        const double gw = x2 * fast_pow35_nonneg(R * inv_x3);
-        R = nb_max0(R + u1[0] + gw);
+        for (int j = 0; j < C2 - 1; ++j) u2[j] = fma(o2[j], p_r, u2[j + 1]);
+        u2[C2 - 1] = o2[C2 - 1] * p_r;
+        const double gw = x2 * pow35_sane(R * inv_x3, k);
+        R = max0_sane((R + u1[0]) + gw);
         const double v = R * inv_x3;
         const double vv = v * v;
-        const double q_r = R * (1.0 - fast_rsqrt4_ge1(fma(vv, vv, 1.0)));
+        const double q_r = fma(-R, rsqrt4_sane(fma(vv, vv, 1.0), k), R);
         R = R - q_r;
-        return q_r + nb_max0(u2[0] + gw);
+        return q_r + max0_sane(u2[0] + gw);
     }
 };
+
+// step dispatch on a compile-time tag (ic<1> = FAST step), usable from generic lambdas for member types
+// without a FAST step
+template <class M>
+__device__ __forceinline__ double gr4j_step(ic<1>, M& m, double P, double E, uint32_t tb, const Exp2Regs& k) {
+    return m.step_fast(P, E, tb, k);
+}
+template <class M>
+__device__ __forceinline__ double gr4j_step(ic<0>, M& m, double P, double E, uint32_t tb, const Exp2Regs&) {
+    return m.step(P, E, tb);
+}
 
 // unit-hydrograph capacity classes used by the kernels
 using Gr4jUh3F = Gr4jMember<3, 7, RRB_MATH_FAST_>;

@@ -60,6 +60,17 @@ inline int cema_TT(int LC) { return kCemaTileDoubles / cema_R(LC); }
 
 inline int64_t padded_steps(int64_t T, int TT) { return ((T + TT - 1) / TT) * TT; }
 
+// The GR4J / Cemaneige-family packers append one flag word to the packed forcing: non-zero when a forcing value is
+// not finite or beyond +-1e6 (then the FAST kernels run the reference-order arithmetic, rr_gr4j.cuh).
+constexpr size_t kForcingFlagBytes = 16;
+inline size_t forcing_bytes(int64_t T, int TT, int R) {
+    return sizeof(double) * (size_t)padded_steps(T, TT) * (size_t)R + kForcingFlagBytes;
+}
+template <class D>
+inline uint32_t* forcing_flag(D* F, int64_t T, int TT, int R) {
+    return reinterpret_cast<uint32_t*>(const_cast<double*>(F) + padded_steps(T, TT) * R);
+}
+
 // ---- forcing packers (device pointers in, packed F[Tpad][R] out) ----
 cudaError_t pack_abc(const double* prec, int64_t T, double* F, cudaStream_t s);
 // count catchments: inputs are [count][T] (PE_m, T_m: [count][12]), F is [count][Tpad][R]

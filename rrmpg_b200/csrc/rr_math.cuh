@@ -290,6 +290,84 @@ __device__ __forceinline__ double fast_pow35_nonneg(double w) {
     return (w == 0.0) ? 0.0 : ((w > 1e300) ? w : r);
 }
 
+// ----------------------------------------------------------------------------------------
+// Branch-free variants for SANE operands (finite, moderately ranged; the kernels establish that once
+// per CTA before the time loop -- Gr4jMember::sane -- and run the reference-order arithmetic otherwise).
+// No special-value handling lives in the time loop: a step is one basic block, so the scheduler can
+// overlap the production-store and routing-store chains, and every fp64 instruction saved is two
+// issue slots.  Seeds come from MUFU.RCP64H / MUFU.RSQ64H (~2^-20 relative); one third-order
+// correction takes them below 2 ulp.
+// ----------------------------------------------------------------------------------------
+struct Exp2Regs {
+    double c0, c1, c2, c3, c4;  // (2^r - 1)/r, degree 4
+    double k5_32, k3_8;         // 5/32, 3/8: multiplier constants of the third-order corrections (an FMA takes one immediate)
+};
+__device__ __forceinline__ Exp2Regs load_exp2_regs(uint32_t tb_addr) {
+    const uint32_t c = tb_addr + (uint32_t)offsetof(FastTables, exp2poly);
+    double k5_32 = 0.15625, k3_8 = 0.375;
+    asm volatile("" : "+d"(k5_32), "+d"(k3_8));  // opaque: held in registers instead of re-materialised per use
+    return Exp2Regs{lds_f64_at(c), lds_f64_at(c + 8), lds_f64_at(c + 16), lds_f64_at(c + 24), lds_f64_at(c + 32), k5_32, k3_8};
+}
+// clamps on the high word of a non-negative double (integer min / max: one ALU instruction)
+__device__ __forceinline__ double clamp_hi_le(double x, int hi_cap) {
+    return __hiloint2double(min(__double2hiint(x), hi_cap), __double2loint(x));
+}
+__device__ __forceinline__ double clamp_hi_ge(double x, int hi_floor) {
+    return __hiloint2double(max(__double2hiint(x), hi_floor), __double2loint(x));
+}
+// numba's max(0, x) for a non-NaN x through the sign bit: ISETP + 2 SEL instead of DSETP + 2 SEL
+__device__ __forceinline__ double max0_sane(double x) { return (__double2hiint(x) < 0) ? 0.0 : x; }
+
+// 2^z - 1 for finite z >= 0 (z is capped just above 64, where tanh has long been 1)
+__device__ __forceinline__ double exp2m1_sane(double z, uint32_t tb_addr, const Exp2Regs& k) {
+    constexpr double kShift = 0x1.8p52 / tables::kExpN;
+    z = clamp_hi_le(z, 0x40500000);  // 64.0
+    double kd = z + kShift;
+    const uint32_t ki = (uint32_t)__double2loint(kd);
+    kd -= kShift;
+    const double r = z - kd;
+    const uint32_t j8 = (ki & (tables::kExpN - 1)) * 8u;
+    uint32_t tlo, thi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                 : "=r"(tlo), "=r"(thi)
+                 : "r"(tb_addr + (uint32_t)offsetof(FastTables, exp2tab) + j8));
+    const double scale = __hiloint2double((int)(thi + (ki << 13)), (int)tlo);
+    double m1;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(m1) : "r"(tb_addr + (uint32_t)offsetof(FastTables, exp2m1tab) + j8));
+    const double base = (ki < (uint32_t)tables::kExpN) ? m1 : scale - 1.0;
+    const double r2 = r * r;
+    const double a = fma(r, k.c1, k.c0);
+    double b = fma(r, k.c3, k.c2);
+    b = fma(r2, k.c4, b);
+    const double t = fma(r2, b, a);
+    return fma(scale, r * t, base);
+}
+// 1 / den for a positive normal den: y (1 + e + e^2), e = 1 - den y
+__device__ __forceinline__ double rcp_sane(double den) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+    const double e = fma(-den, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+}
+// v^(-1/4) for 1 <= v < 2^1000: y (1 + e/4 + 5 e^2/32), e = 1 - v y^4
+__device__ __forceinline__ double rsqrt4_sane(double v, const Exp2Regs& k) {
+    const double a = rsqrt_approx_f64(v);
+    const double y = a * rsqrt_approx_f64(a);
+    const double y2 = y * y;
+    const double e = fma(-v, y2 * y2, 1.0);
+    return fma(y, e * fma(e, k.k5_32, 0.25), y);
+}
+// w^3.5 = w^4 w^(-1/2) for finite w >= 0 (w = 0 -> 0: the seed operand is floored at 2^-1021, w^4 underflows)
+__device__ __forceinline__ double pow35_sane(double w, const Exp2Regs& k) {
+    const double wc = clamp_hi_ge(w, 0x00200000);
+    const double y0 = rsqrt_approx_f64(wc);
+    const double t = wc * y0;
+    const double e = fma(-t, y0, 1.0);                 // 1 - w y^2
+    const double y = fma(y0 * e, fma(e, k.k3_8, 0.5), y0);  // y (1 + e/2 + 3 e^2/8)
+    const double w2 = w * w;
+    return (w2 * w2) * y;
+}
+
 // stage the tables into shared memory (call by every thread, before a __syncthreads())
 __device__ __forceinline__ const FastTables* fastmath_tables_to_smem(unsigned char* smem_at) {
     FastTables* dst = reinterpret_cast<FastTables*>(smem_at);
