@@ -37,7 +37,8 @@ __global__ void cema_pack_kernel(const double* __restrict__ prec, const double* 
             row[l] = snow;
             row[LC + l] = p - snow;                   // :77
             row[2 * LC + l] = mean_temp[t * L + l];
-            ok = ok && forcing_value_sane(snow) && forcing_value_sane(p - snow) && forcing_value_sane(row[2 * LC + l]);
+            ok = ok && forcing_value_sane(snow) && forcing_value_sane(p - snow) && forcing_value_sane(row[2 * LC + l]) &&
+                 snow >= 0.0 && p - snow >= 0.0;
         }
         if (etp) {
             row[3 * LC] = etp[t];

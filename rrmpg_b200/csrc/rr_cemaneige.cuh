@@ -86,16 +86,12 @@ __global__ void cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
     double omCTG = 1 - CTG;  // loop invariant of cemaneige_model.py:94
     pin(omCTG);
     if (EXACT) L = LC;
-    double G[LC], eTG[LC], gt[LC], inv_gt[LC];
-    uint32_t gt_span[LC];
+    double G[LC], eTG[LC];
     double sca_prev[HYST ? LC : 1], swe_max[HYST ? LC : 1], thmelt[HYST ? LC : 1], fice[ICE ? LC : 1];
 #pragma unroll
     for (int l = 0; l < LC; ++l) {
         G[l] = 0.0;
         eTG[l] = 0.0;
-        gt[l] = (l < L) ? a.g_tresh[l] : 0.0;
-        inv_gt[l] = 1.0 / gt[l];
-        gt_span[l] = div_invariant_span(gt[l]);
         if (HYST) {
             // sca[t-1] at t = 0 is sca[T-1], still 0 from np.zeros -- or sca_init itself when T == 1 (:126)
             sca_prev[l] = (a.T == 1) ? a.sca0 : 0.0;
@@ -141,16 +137,56 @@ __global__ void cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
     pin(inv_layers);
 
     extern __shared__ __align__(128) unsigned char rrb_smem[];
+    // G_tresh is a property of the catchment, not of the member: {G_tresh, 1/G_tresh, division span} per layer
+    // live in shared memory and are only read by the steps that really divide by it
+    uint32_t gtrec = 0;
+    if constexpr (!HYST) {
+        double* rec = reinterpret_cast<double*>(rrb_smem + forcing_smem_bytes<R, TT>());
+        if ((int)threadIdx.x < LC) {
+            const int l = threadIdx.x;
+            const double gt = (l < L) ? a.g_tresh[l] : 0.0;
+            rec[4 * l] = gt;
+            rec[4 * l + 1] = 1.0 / gt;
+            reinterpret_cast<uint32_t*>(rec + 4 * l + 2)[0] = div_invariant_span(gt);
+        }
+        gtrec = smem_u32(rec);
+        pin(gtrec);
+        __syncthreads();
+    }
+    constexpr size_t kGtBytes = HYST ? 0 : 32 * LC;
+    // ---- Snow-routine contract (plain Cemaneige routine only).  When, for every member of the CTA, Kf >= 0, the
+    // parameters and initial states are finite and moderately ranged, the pack starts non-negative, the packed
+    // forcing is finite with non-negative snow and rain (flag of the packer) and every G_tresh is 0 or within
+    // [2^-60, 2^60], then the pack stays in [0, 1e13] for the whole series and the time step needs no special
+    // cases: G / G_tresh by the Markstein sequence without range checks (for a pack below 2^-960 the quotient
+    // is below 2^-900 whatever its low bits, and 0.9 ratio + 0.1 rounds to 0.1 as in the reference), evaluated
+    // unconditionally like the reference does.  Bit-identical to the general step; one basic block for all
+    // layers.  Any other CTA runs the general step.
+    bool snow_ok = false;
+    if constexpr (!HYST) {
+        snow_ok = Kf >= 0.0 && Kf <= 1e6 && fabs(CTG) <= 1e6 && a.g0 >= 0.0 && a.g0 <= 1e6 && fabs(a.e0) <= 1e6 &&
+                  *a.fflag == 0u;
+#pragma unroll
+        for (int l = 0; l < LC; ++l) {
+            if (l < L) {
+                const double gt = lds_f64(gtrec + 32u * l);
+                uint32_t span;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(span) : "r"(gtrec + 32u * l + 16u));
+                snow_ok = snow_ok && (span != 0u || gt == 0.0) && G[l] >= 0.0 && G[l] <= 1e13 && fabs(eTG[l]) <= 1e6;
+            }
+        }
+    }
     uint32_t tb = 0;
     bool use_fast = false;
     Exp2Regs ek{};
     if constexpr (COUPLED && FAST) {
-        tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<R, TT>()));
+        tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<R, TT>() + kGtBytes));
         pin(tb);
         // FAST path contract of Gr4jMember: finite, moderately ranged parameters, initial states and forcing --
         // then the snow routine feeds GR4J finite water.  CTA-uniform; the barrier also publishes the tables
         // (the peeled first step below already reads them).
-        bool sane = gr.sane && *a.fflag == 0u && fabs(a.g0) <= 1e6 && fabs(a.e0) <= 1e6 && fabs(a.sca0) <= 1e6;
+        bool sane = gr.sane && *a.fflag == 0u && fabs(a.g0) <= 1e6 && fabs(a.e0) <= 1e6 && fabs(a.sca0) <= 1e6 &&
+                    (HYST || snow_ok);
         for (int k = 0; k < (int)a.pstride; ++k) sane = sane && fabs(p[k]) <= 1e6;
         if (ICE) {
 #pragma unroll
@@ -161,12 +197,15 @@ __global__ void cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
             ek = load_exp2_regs(tb);
             gr.enter_fast();
         }
+    } else if constexpr (!COUPLED && !HYST) {
+        use_fast = __syncthreads_and(snow_ok) != 0;  // standalone Cemaneige: the contract step in both math modes
     }
 
     // one timestep; FIRST = the very first step of the series, where the stores take their initial values
     // instead of being updated (cemaneige_model.py:85-92, cemaneigehyst_model.py:107-115)
-    auto step = [&](auto first_c, auto fast_c, int64_t t, const double* f) {
+    auto step = [&](auto first_c, auto fast_c, auto snow_c, int64_t t, const double* f) {
         constexpr bool FIRST = decltype(first_c)::value != 0;
+        constexpr bool CONTRACT = decltype(snow_c)::value != 0;
         double lw_sum = 0.0, ice_sum = 0.0;
 #pragma unroll
         for (int l = 0; l < LC; ++l) {
@@ -175,20 +214,43 @@ __global__ void cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
                 double g = FIRST ? a.g0 : G[l] + snow;                    // :85-88
                 double e = FIRST ? a.e0 : CTG * eTG[l] + omCTG * Tm;      // :91-94
                 e = (e > 0) ? 0.0 : e;                                    // :95-96
-                // potential melt (:99-106), branch-free
-                const double kt = Kf * Tm;
-                const double capped = (kt > g) ? g : kt;
-                const double pot = (e == 0 && Tm > 0) ? capped : 0.0;
                 double melt;
-                if constexpr (!HYST) {
+                if constexpr (!HYST && CONTRACT) {
+                    // contract step (see above): every operation of :99-115, no special cases
+                    const double kt = Kf * Tm;
+                    const double capped = (kt > g) ? g : kt;
+                    const double pot = (e == 0 && Tm > 0) ? capped : 0.0;
+                    const double2 gi = lds_f64x2(gtrec + 32u * l);        // {G_tresh, 1 / G_tresh}
+                    double q = g * gi.y;
+                    double r = fma(-gi.x, q, g);
+                    q = fma(r, gi.y, q);
+                    r = fma(-gi.x, q, g);
+                    q = fma(r, gi.y, q);                                   // RN(G / G_tresh), div_by_invariant
+                    const double ratio = (g < gi.x) ? q : 1.0;             // :109-112
+                    melt = (0.9 * ratio + 0.1) * pot;                      // :115
+                } else if constexpr (!HYST) {
+                    // potential melt (:99-106), branch-free
+                    const double kt = Kf * Tm;
+                    const double capped = (kt > g) ? g : kt;
+                    const double pot = (e == 0 && Tm > 0) ? capped : 0.0;
                     // snow-covered-area ratio (:109-112).  The division is only evaluated where it can change
                     // the result: with pot == 0 and a non-negative pack the product (0.9 ratio + 0.1) * pot is
                     // +0 for every ratio in [0, 1] (the sign-bit test over-approximates "G < 0": harmless).
                     double ratio = 1.0;
-                    if (g < gt[l] && (pot != 0.0 || __double2hiint(g) < 0))
-                        ratio = div_by_invariant(g, gt[l], inv_gt[l], gt_span[l]);
+                    if (pot != 0.0 || __double2hiint(g) < 0) {
+                        const double2 gi = lds_f64x2(gtrec + 32u * l);    // {G_tresh, 1 / G_tresh}
+                        if (g < gi.x) {
+                            uint32_t span;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(span) : "r"(gtrec + 32u * l + 16u));
+                            ratio = div_by_invariant(g, gi.x, gi.y, span);
+                        }
+                    }
                     melt = (0.9 * ratio + 0.1) * pot;                     // :115
                 } else {
+                    // potential melt (cemaneigehyst_model.py:117-128), branch-free
+                    const double kt = Kf * Tm;
+                    const double capped = (kt > g) ? g : kt;
+                    const double pot = (e == 0 && Tm > 0) ? capped : 0.0;
                     // SWE-SCA hysteresis (cemaneigehyst_model.py:131-160)
                     const double bal = snow - pot;                        // :131
                     double sca;
@@ -258,24 +320,27 @@ __global__ void cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
         }
     };
 
-    auto run = [&](auto fast_c) {
+    auto run = [&](auto fast_c, auto snow_c) {
         int64_t t_first = slab.t_begin;
         if (slab.t_begin == 0 && slab.t_end > 0) {  // t = 0 peeled: its forcing row comes straight from global memory
             double f0[R];
 #pragma unroll
             for (int k = 0; k < R; ++k) f0[k] = F[k];
-            step(ic<1>{}, fast_c, 0, f0);
+            step(ic<1>{}, fast_c, snow_c, 0, f0);
             t_first = 1;
         }
         stream_forcing_grouped<R, TT, 1, CemaF<LC>>(F, t_first, slab.t_end, [&](auto, int64_t t, const CemaF<LC>* fp) {
-            step(ic<0>{}, fast_c, t, fp[0].v);
+            step(ic<0>{}, fast_c, snow_c, t, fp[0].v);
         });
     };
     if constexpr (COUPLED && FAST) {
-        if (use_fast) run(ic<1>{});
-        else run(ic<0>{});
+        if (use_fast) run(ic<1>{}, ic<HYST ? 0 : 1>{});
+        else run(ic<0>{}, ic<0>{});
+    } else if constexpr (!COUPLED && !HYST) {
+        if (use_fast) run(ic<0>{}, ic<1>{});
+        else run(ic<0>{}, ic<0>{});
     } else {
-        run(ic<0>{});
+        run(ic<0>{}, ic<0>{});
     }
 
     if (gi < N) {
@@ -318,7 +383,8 @@ static cudaError_t cema_launch_variant(const CemaArgs& a, const CemaOut& out, co
     constexpr int R = CemaGeom<LC>::R, TT = CemaGeom<LC>::TT;
     const int block = cfg.block > 0 ? cfg.block : pick_block(a.N, cfg.sm_count, 128);
     const unsigned grid = (unsigned)((a.N + block - 1) / block);
-    const size_t smem = forcing_smem_bytes<R, TT>() + ((FAST && Gr4j::kStateSlots > 0) ? fastmath_smem_bytes() : 0);
+    const size_t smem = forcing_smem_bytes<R, TT>() + ((FAMILY & 1) ? 0 : 32 * LC) +
+                        ((FAST && Gr4j::kStateSlots > 0) ? fastmath_smem_bytes() : 0);
     const bool plain = out.q && !out.G && !obj.qobs;
 #define RRB_CEMA(P_, E_) cema_kernel<LC, Gr4j, FAST, P_, E_, FAMILY><<<grid, block, smem, cfg.stream>>>(a, out, slab, obj)
     if (FAMILY == 0) {

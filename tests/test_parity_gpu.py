@@ -249,6 +249,62 @@ def test_nan_propagation_matches_oracle():
     assert_close(q, ref, "hbvedu NaN members")
 
 
+def test_gr4j_fast_path_contract_falls_back_to_reference_arithmetic():
+    """The FAST GR4J step has no special-value handling; CTAs with a member outside its contract (or a
+    non-finite / huge forcing value anywhere in the series) run the reference-order step instead.  Both
+    routes must agree with the oracle, NaN mask included."""
+    f = synthetic.forcing(400)
+    P = synthetic.random_params(GR4J(), 200, seed=5)
+    P["x1"][3] = 1e-5      # S/x1 astronomically large: (1 + u^4) overflows in the reference too
+    P["x3"][70] = np.nan
+    P["x2"][131] = 1e9
+    P["x1"][199] = -20.0   # negative capacity: tanh of a negative argument, negative stores
+    ref = oracle.gr4j(f["prec"], f["etp"], 0.6, 0.7, P, return_storage=True)
+    got = engine.gr4j(f["prec"], f["etp"], 0.6, 0.7, P, return_storage=True, math="fast")
+    for nm, r in zip(["qsim", "s_store", "r_store"], ref):
+        assert_close(got[nm], r, "gr4j insane members " + nm)
+    # non-finite and huge forcing: every CTA takes the reference-order step
+    P = synthetic.random_params(GR4J(), 100, seed=6)
+    for bad in (np.nan, np.inf, 1e9):
+        etp = f["etp"].copy(); etp[250] = bad
+        prec = f["prec"].copy(); prec[300] = abs(bad) if np.isfinite(bad) else f["prec"][300]
+        ref = oracle.gr4j(prec, etp, 0.6, 0.7, P)
+        got = engine.gr4j(prec, etp, 0.6, 0.7, P, math="fast")["qsim"]
+        assert_close(got, ref, f"gr4j forcing with {bad}")
+    # zero stores, zero rain, x2 strongly negative (routing store clamps at 0 -> w = 0 in w^3.5)
+    P = synthetic.random_params(GR4J(), 64, seed=7)
+    P["x2"][:] = -50.0
+    ref = oracle.gr4j(f["prec"] * 0, f["etp"], 0.0, 0.0, P, return_storage=True)
+    got = engine.gr4j(f["prec"] * 0, f["etp"], 0.0, 0.0, P, return_storage=True, math="fast")
+    for nm, r in zip(["qsim", "s_store", "r_store"], ref):
+        assert_close(got[nm], r, "gr4j dry catchment " + nm)
+    # an extreme storm relative to a tiny production store: tanh saturates (argument clamp of the FAST path)
+    P = synthetic.random_params(GR4J(), 64, seed=8)
+    P["x1"][:] = np.linspace(0.01, 5.0, 64)
+    prec = f["prec"].copy(); prec[100:110] = 5000.0
+    ref = oracle.gr4j(prec, f["etp"], 0.6, 0.7, P)
+    got = engine.gr4j(prec, f["etp"], 0.6, 0.7, P, math="fast")["qsim"]
+    assert_close(got, ref, "gr4j saturated tanh")
+
+
+def test_cemaneigegr4j_fast_path_contract_falls_back_to_reference_arithmetic():
+    c = load_golden("ensemble_cemaneige")
+    g = load_golden("ensemble_cemaneigegr4j")
+    Pm = np.array(g["params"], copy=True)   # [N, 6] = (CTG, Kf, x1, x2, x3, x4)
+    Pm[1, 1] = np.nan      # Kf: NaN melt -> NaN water into GR4J
+    Pm[5, 2] = 1e-6        # x1 outside the FAST contract
+    for etp_bad in (None, np.nan):
+        etp = g["etp"].copy()
+        if etp_bad is not None:
+            etp[77] = etp_bad
+        ref = oracle.cemaneigegr4j(c["layer_prec"], c["layer_mean_temp"], etp, c["frac_solid"], g["inits"], Pm,
+                                   return_storages=True)
+        got = engine.cemaneigegr4j(c["layer_prec"], c["layer_mean_temp"], etp, c["frac_solid"], g["inits"], Pm,
+                                   return_storages=True, math="fast")
+        for nm, r in zip(["qsim", "G", "eTG", "s_store", "r_store"], ref):
+            assert_close(got[nm], r, f"cemaneigegr4j insane ({etp_bad}) " + nm)
+
+
 # ------------------------------------------------------------------ time-slab pipeline, objective, device mode
 @pytest.mark.parametrize("slab", [1, 7, 128, 300])
 def test_time_slab_pipeline_is_bit_identical_to_one_launch(slab):
