@@ -545,7 +545,7 @@ int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* mo
     double in4[4];
     memcpy(in4, inits, sizeof(in4));  // inits is host memory in both modes
     void* F;
-    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, kHbvTT) * kHbvR, &F))) return rc;
+    if ((rc = P.c->ensure(B_F, forcing_bytes(T, kHbvTT, kHbvR), &F))) return rc;
     RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.o.math, 1, P.s));
     Job job;
     job.T = T; job.N = N;
@@ -555,7 +555,8 @@ int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* mo
     const double i0 = in4[0], i1 = in4[1], i2 = in4[2], i3 = in4[3];
     job.launch = [=](const Slab& sl, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
         const double in[4] = {i0, i1, i2, i3};
-        return launch_hbvedu((const double*)F, T, in, dp, N, out[0], out[1], out[2], out[3], out[4], sl, ob, cfg);
+        return launch_hbvedu((const double*)F, T, in, dp, N, out[0], out[1], out[2], out[3], out[4], sl, ob, cfg,
+                             forcing_flag((const double*)F, T, kHbvTT, kHbvR));
     };
     return run_job(*P.c, P.o, job, P.d_qobs, P.d_mse);
 }
@@ -602,8 +603,9 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
     }
     const int64_t Tpad = padded_steps(T, kHbvTT);
     void* F;
-    if ((rc = c.ensure(B_F, sizeof(double) * (size_t)(C * Tpad) * kHbvR, &F))) return rc;
+    if ((rc = c.ensure(B_F, sizeof(double) * (size_t)(C * Tpad) * kHbvR + kForcingFlagBytes, &F))) return rc;
     RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.o.math, (int)C, P.s));
+    const uint32_t* hbv_flag = reinterpret_cast<const uint32_t*>((const double*)F + C * Tpad * kHbvR);
 
     LaunchCfg cfg{};
     cfg.block = P.o.block;
@@ -617,7 +619,8 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
         Batch b{(int)C, Tpad * kHbvR, T * N, (const double*)d_inits};
         Slab slab{0, T, 0, nullptr, 0};
         Objective obj{P.d_qobs, P.d_mse, T};
-        RRB_CUDA(launch_hbvedu((const double*)F, T, zero4, P.d_params, N, qsim, snow, soil, s1, s2, slab, obj, cfg, b));
+        RRB_CUDA(launch_hbvedu((const double*)F, T, zero4, P.d_params, N, qsim, snow, soil, s1, s2, slab, obj, cfg,
+                               hbv_flag, b));
         return RRB_OK;
     }
     // host buffers: chunks of catchments through a two-deep device ring; the D2H of chunk k overlaps the
@@ -644,7 +647,7 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
         Slab slab{0, T, 0, nullptr, 0};
         Objective obj{P.d_qobs ? P.d_qobs + c0 * T : nullptr, P.d_mse ? P.d_mse + c0 * N : nullptr, T};
         RRB_CUDA(launch_hbvedu((const double*)F + c0 * Tpad * kHbvR, T, zero4, P.d_params + c0 * N * 11, N, dev[sidx][0],
-                               dev[sidx][1], dev[sidx][2], dev[sidx][3], dev[sidx][4], slab, obj, cfg, b));
+                               dev[sidx][1], dev[sidx][2], dev[sidx][3], dev[sidx][4], slab, obj, cfg, hbv_flag, b));
         RRB_CUDA(cudaEventRecord(c.ev_done[sidx], c.compute));
         RRB_CUDA(cudaStreamWaitEvent(c.copy, c.ev_done[sidx], 0));
         for (int j = 0; j < 5; ++j)

@@ -26,7 +26,7 @@ namespace rrb {
 __global__ void hbv_pack_kernel(const double* __restrict__ temp, const double* __restrict__ prec,
                                 const int8_t* __restrict__ month0, const double* __restrict__ PE_m,
                                 const double* __restrict__ T_m, int64_t T, int64_t Tpad, int fast,
-                                double* __restrict__ F) {
+                                double* __restrict__ F, uint32_t* __restrict__ fflag) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= Tpad) return;
     const int64_t c = blockIdx.y;  // catchment
@@ -40,6 +40,7 @@ __global__ void hbv_pack_kernel(const double* __restrict__ temp, const double* _
         v.z = temp[t] - T_m[m];
         v.w = PE_m[m];
         if (fast) v.z = v.z * v.w;
+        if (!(fabs(v.y) <= 1e300)) atomicOr(fflag, 1u);  // inf / NaN precipitation: FAST contract broken
     }
     reinterpret_cast<double4*>(F)[t] = v;
 }
@@ -47,8 +48,11 @@ __global__ void hbv_pack_kernel(const double* __restrict__ temp, const double* _
 cudaError_t pack_hbvedu(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
                         const double* T_m, int64_t T, double* F, int math, int count, cudaStream_t s) {
     int64_t Tpad = padded_steps(T, kHbvTT);
-    hbv_pack_kernel<<<dim3((unsigned)((Tpad + 255) / 256), (unsigned)count), 256, 0, s>>>(temp, prec, month0, PE_m, T_m, T,
-                                                                                      Tpad, math == RRB_MATH_FAST_, F);
+    uint32_t* fflag = reinterpret_cast<uint32_t*>(F + (int64_t)count * Tpad * kHbvR);
+    cudaError_t e = cudaMemsetAsync(fflag, 0, kForcingFlagBytes, s);
+    if (e != cudaSuccess) return e;
+    hbv_pack_kernel<<<dim3((unsigned)((Tpad + 255) / 256), (unsigned)count), 256, 0, s>>>(
+        temp, prec, month0, PE_m, T_m, T, Tpad, math == RRB_MATH_FAST_, F, fflag);
     return cudaGetLastError();
 }
 
@@ -92,7 +96,9 @@ static __device__ __noinline__ double hbv_slow_pow(double soil, double FC, doubl
 template <bool WRITEQ, bool STORAGE, bool OBJ>
 __global__ void hbv_precise_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                                    const double* __restrict__ params, int64_t N, HbvOut out, Slab slab,
-                                   Objective obj, Batch batch) {
+                                   Objective obj, Batch batch, const uint32_t* __restrict__ only_if_flag, int fast_packing) {
+    // launched behind the FAST kernel: do the work only when that one declined it (see hbv_fast_kernel)
+    if (only_if_flag && *only_if_flag == 0u) return;
     HBV_BATCH_PROLOGUE
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     // threads past the end of the ensemble recompute member N-1 and store the same values to the same
@@ -143,7 +149,8 @@ __global__ void hbv_precise_kernel(const double* __restrict__ F, double snow0, d
         const double snow_new = cold ? snow + f.prec : nb_max0(snow - m);
         const double liquid = cold ? 0.0 : f.prec + nb_min(snow, m);
         const double prec_eff = liquid * pow(soil / FC, Beta);              // :99
-        const double pe = (1 + C * f.dT) * f.PEm;                           // :102
+        // (FAST packing holds dT * PEm in the dT slot: pe = PEm + C (dT PEm) -- only reached for non-finite rain)
+        const double pe = fast_packing ? f.PEm + C * f.dT : (1 + C * f.dT) * f.PEm;  // :102
         const double ea = (soil > PWP) ? pe : pe * (soil / PWP);            // :105-108
         const double soil_new = soil + liquid - prec_eff - ea;              // :111
         const double over = nb_max0(s1 - L);
@@ -208,7 +215,10 @@ constexpr int kHbvGroup = RRB_HBV_GROUP;
 template <bool WRITEQ, bool STORAGE, bool OBJ>
 __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                                 const double* __restrict__ params, int64_t N, HbvOut out, Slab slab,
-                                Objective obj, Batch batch) {
+                                Objective obj, Batch batch, const uint32_t* __restrict__ fflag) {
+    // FAST contract: finite precipitation (the snow routine below forms prec - prec for "no liquid water").  The
+    // packer flags anything else and the PRECISE kernel launched right behind this one takes the whole launch.
+    if (*fflag != 0u) return;
     HBV_BATCH_PROLOGUE
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t i = gi < N ? gi : N - 1;  // see hbv_precise_kernel
@@ -276,14 +286,16 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
             // predicate: snow - m > 0 <=> m < snow for every operand pair (NaN and inf included).
 #pragma unroll
             for (int g = 0; g < G; ++g) {
+                // melt = min(snow, DD (temp - T_t)) serves both max(0, snow - m) = snow - melt and the liquid water
+                // prec + melt; the cold branch (snow + prec, no liquid water) is the same two additions with
+                // -prec in place of melt: snow - (-prec) and prec + (-prec) = +0 for finite precipitation
                 const double m = DD * (f[g].temp - T_t);
-                const bool melt_all = !(m < snow);
-                const double melt_snow = melt_all ? 0.0 : snow - m;
-                const double melt_liq = f[g].prec + (melt_all ? snow : m);
+                const double melt = (m < snow) ? m : snow;
                 const bool cold = f[g].temp < T_t;
-                const double acc_snow = snow + f[g].prec;
-                snow = cold ? acc_snow : melt_snow;
-                liquid[g] = cold ? 0.0 : melt_liq;
+                const double nprec = __hiloint2double(__double2hiint(f[g].prec) ^ (int)0x80000000, __double2loint(f[g].prec));
+                const double sel = cold ? nprec : melt;
+                snow = snow - sel;
+                liquid[g] = f[g].prec + sel;
                 snow_g[g] = snow;
                 pe[g] = fma(C, f[g].dT, f[g].PEm);  // FAST packing: dT holds dT * PEm
             }
@@ -358,7 +370,7 @@ int state_slots_hbvedu() { return 5; }
 
 cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, const double* params, int64_t N,
                           double* qsim, double* snow, double* soil, double* s1, double* s2, const Slab& slab,
-                          const Objective& obj, const LaunchCfg& cfg, const Batch& batch) {
+                          const Objective& obj, const LaunchCfg& cfg, const uint32_t* fflag, const Batch& batch) {
     (void)T;
     if (N <= 0 || batch.count <= 0) return cudaSuccess;
     const int block = cfg.block > 0 ? cfg.block : pick_block(N * batch.count, cfg.sm_count, N >= 256 ? 256 : 64);
@@ -369,7 +381,7 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
     HbvOut out{qsim, snow, soil, s1, s2};
 #define RRB_HBV(M_, Q_, S_, O_)                                                                                   \
     M_<Q_, S_, O_><<<grid, block, smem, cfg.stream>>>(F, inits4[0], inits4[1], inits4[2], inits4[3], params, N, out, \
-                                                      slab, obj, batch)
+                                                      slab, obj, batch, RRB_HBV_TAIL)
 #define RRB_HBV_M(M_)                                      \
     do {                                                   \
         if (wq && st && ob) RRB_HBV(M_, true, true, true);        \
@@ -380,8 +392,21 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
         else if (st) RRB_HBV(M_, false, true, false);             \
         else RRB_HBV(M_, false, false, true);                     \
     } while (0)
-    if (fast) RRB_HBV_M(hbv_fast_kernel);
-    else RRB_HBV_M(hbv_precise_kernel);
+    if (fast) {
+#define RRB_HBV_TAIL fflag
+        RRB_HBV_M(hbv_fast_kernel);
+#undef RRB_HBV_TAIL
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        // the fallback for a flagged forcing block: exits at once otherwise (FAST packing: dT slot = dT * PEm)
+#define RRB_HBV_TAIL fflag, 1
+        RRB_HBV_M(hbv_precise_kernel);
+#undef RRB_HBV_TAIL
+    } else {
+#define RRB_HBV_TAIL nullptr, 0
+        RRB_HBV_M(hbv_precise_kernel);
+#undef RRB_HBV_TAIL
+    }
 #undef RRB_HBV_M
 #undef RRB_HBV
     return cudaGetLastError();

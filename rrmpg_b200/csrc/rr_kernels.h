@@ -73,7 +73,8 @@ inline uint32_t* forcing_flag(D* F, int64_t T, int TT, int R) {
 
 // ---- forcing packers (device pointers in, packed F[Tpad][R] out) ----
 cudaError_t pack_abc(const double* prec, int64_t T, double* F, cudaStream_t s);
-// count catchments: inputs are [count][T] (PE_m, T_m: [count][12]), F is [count][Tpad][R]
+// count catchments: inputs are [count][T] (PE_m, T_m: [count][12]), F is [count][Tpad][R] followed by the flag word
+// (non-zero: a precipitation value is not finite -- the FAST kernel then leaves the launch to the PRECISE one)
 cudaError_t pack_hbvedu(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
                         const double* T_m, int64_t T, double* F, int math, int count, cudaStream_t s);
 cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* F, cudaStream_t s);
@@ -87,7 +88,8 @@ cudaError_t launch_abc(const double* F, int64_t T, double s0, const double* para
 
 cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, const double* params, int64_t N,
                           double* qsim, double* snow, double* soil, double* s1, double* s2, const Slab& slab,
-                          const Objective& obj, const LaunchCfg& cfg, const Batch& batch = Batch{1, 0, 0, nullptr});
+                          const Objective& obj, const LaunchCfg& cfg, const uint32_t* fflag,
+                          const Batch& batch = Batch{1, 0, 0, nullptr});
 
 // uh_cap: 0 = derive from x4_max
 cudaError_t launch_gr4j(const double* F, int64_t T, double s_init, double r_init, const double* params,

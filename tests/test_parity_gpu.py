@@ -249,6 +249,22 @@ def test_nan_propagation_matches_oracle():
     assert_close(q, ref, "hbvedu NaN members")
 
 
+def test_hbvedu_non_finite_precipitation_takes_the_reference_order_kernel():
+    """The FAST HBV snow routine forms prec - prec for "no liquid water", exact for finite rain only; the packer
+    flags inf / NaN precipitation and the PRECISE kernel launched behind the FAST one takes the launch."""
+    f = synthetic.forcing(300)
+    P = synthetic.random_params(HBVEdu(), 70, seed=3)
+    for bad in (np.nan, np.inf):
+        prec = f["prec"].copy()
+        prec[int(np.argmin(f["temp"][:200]))] = bad   # a cold day: the reference stores it as snow, no liquid water
+        prec[250] = bad
+        ref = oracle.hbvedu(f["temp"], prec, f["month"] - 1, f["PE_m"], f["T_m"], (0, 100, 3, 10), P, return_storage=True)
+        got = engine.hbvedu(f["temp"], prec, f["month"] - 1, f["PE_m"], f["T_m"], (0, 100, 3, 10), P, return_storage=True,
+                            math="fast")
+        for nm, r in zip(["qsim", "snow", "soil", "s1", "s2"], ref):
+            assert_close(got[nm], r, f"hbvedu prec={bad} {nm}")
+
+
 def test_gr4j_fast_path_contract_falls_back_to_reference_arithmetic():
     """The FAST GR4J step has no special-value handling; CTAs with a member outside its contract (or a
     non-finite / huge forcing value anywhere in the series) run the reference-order step instead.  Both
@@ -536,3 +552,37 @@ def test_full_size_cemaneigegr4j_per_gpu_share():
     fr = oracle.calculate_solid_fraction(p, alts, me, mn, mx)
     ref = oracle.cemaneigegr4j(p, me, f["etp"], fr, (0, 0, 0.6, 0.7), P[idx])
     assert_close(q[:, idx], ref, "cemaneigegr4j 32k sampled columns")
+
+
+def test_full_size_hbvedu_multi_catchment_per_gpu_share():
+    """BASELINE config 5: 1024 catchments x 4096 members over 8 GPUs = 128 catchments per GPU, 10 years hourly
+    (T = 87 660).  The discharge of one GPU's share would be 368 GB, so the run uses the fused objective
+    (device mode, no qsim): one launch, grid.y = catchment.  Sampled members are checked against the oracle."""
+    import torch
+    Cn, N, T = 128, 4096, synthetic.T_HOURLY_10Y
+    dev = torch.device("cuda:0")
+    fs = [synthetic.forcing(T, seed=synthetic.SEED + c, hourly=True) for c in range(Cn)]
+    temp = np.stack([f["temp"] for f in fs]); prec = np.stack([f["prec"] for f in fs])
+    m0 = np.stack([f["month"] - 1 for f in fs]).astype(np.int8)
+    PE = np.stack([f["PE_m"] / 24.0 for f in fs]); TM = np.stack([f["T_m"] for f in fs])
+    P = engine.pack_params(synthetic.random_params(HBVEdu(), Cn * N, seed=77)).reshape(Cn, N, 11)
+    qobs = np.abs(np.random.default_rng(11).normal(0.05, 0.02, (Cn, T)))
+    t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    args = (t(temp), t(prec), t(m0, torch.int8), t(PE), t(TM), (0, 100, 3, 10), t(P))
+    r = engine.hbvedu_multi(*args, qobs=t(qobs), want_qsim=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = engine.hbvedu_multi(*args, qobs=t(qobs), want_qsim=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"\nconfig 5 per-GPU share: {Cn} x {N} members x {T} steps in {ms:.1f} ms = {Cn * N * T / ms / 1e6:.1f} G member-steps/s")
+    mse = r["mse"].cpu().numpy()
+    assert mse.shape == (Cn, N) and np.isfinite(mse).all()
+    rng = np.random.default_rng(4)
+    for c in (0, 63, 127):
+        idx = np.r_[0, N - 1, rng.integers(0, N, 6)]
+        ref = oracle.hbvedu(temp[c], prec[c], m0[c], PE[c], TM[c], (0, 100, 3, 10), P[c, idx])
+        ref_mse = ((qobs[c][:, None] - ref) ** 2).mean(axis=0)
+        np.testing.assert_allclose(mse[c, idx], ref_mse, rtol=1e-9)
