@@ -96,3 +96,60 @@ def barrier():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+def broadcast_series(series, src=0, device=None):
+    """Broadcast a dict of forcing arrays from ``src`` to every rank: ONE object broadcast of the layout
+    (names and shapes, a few hundred bytes) and ONE tensor broadcast of the packed block.  Ranks other than
+    ``src`` may pass ``None``.  Returns the dict (numpy arrays) on every rank."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return {k: np.asarray(v, dtype=np.float64) for k, v in series.items()}
+    rank = dist.get_rank()
+    meta = [None]
+    mat = None
+    if rank == src:
+        mat, layout = pack_forcing(series)
+        meta = [(layout, mat.shape)]
+    dist.broadcast_object_list(meta, src=src)
+    layout, shape = meta[0]
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.as_tensor(mat, device=device) if rank == src else torch.empty(shape, dtype=torch.float64, device=device)
+    broadcast_forcing(t, src=src)
+    return unpack_forcing(t.cpu().numpy(), layout)
+
+
+def simulate_sharded(model, params, series=None, src=0, **kwargs):
+    """``model.simulate`` for this rank's contiguous member block of a global ensemble.
+
+    ``params``: the GLOBAL record array (every rank draws or holds the same one, e.g. from the same seed);
+    ``series``: dict of the time-series arguments of ``model.simulate`` (``prec``, ``temp`` ...), needed on
+    ``src`` only -- it is broadcast once; everything else (scalars, ``altitudes`` ...) goes through ``kwargs``
+    and must be equal on all ranks.  Returns ``(lo, hi, result)`` where ``result`` is what
+    ``model.simulate(params=params[lo:hi])`` returns: columns ``[lo, hi)`` of the global ``[T, N]`` arrays.
+    No collective touches the result; use :func:`gather_members` for small per-member vectors."""
+    rank, _, world = env_world()
+    forcing = broadcast_series(series, src=src) if (series is not None or world > 1) else {}
+    lo, hi = member_block(len(params), rank, world)
+    out = model.simulate(params=params[lo:hi], **forcing, **kwargs)
+    return lo, hi, out
+
+
+def gather_members(local, n_members):
+    """All-gather a per-member vector (e.g. the fused MSE of this rank's block) into the global ``[N]`` order."""
+    import torch
+    import torch.distributed as dist
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return local
+    world = dist.get_world_size()
+    sizes = [member_block(n_members, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    buf = torch.zeros(width, dtype=torch.float64, device=dev)
+    buf[:local.size] = torch.as_tensor(local, device=dev)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    return np.concatenate([p[:hi - lo].cpu().numpy() for p, (lo, hi) in zip(parts, sizes)])
