@@ -190,6 +190,23 @@ RRB_API int rrb_cemaneigehystgr4jice_simulate(const double* prec, const double* 
                                               double* icemelt, double* snowmelt /* nullable x7 */,
                                               const rrb_opts* opts);
 
+/* ---- member-independent layer preprocessing of the Cemaneige family, on the device --------
+ * Replaces extrapolate_precipitation (rrmpg/models/cemaneige_utils.py:101-158), extrapolate_temperature
+ * (:161-208) and calculate_solid_fraction (:16-98), i.e. the [T] -> [T, L] step of Cemaneige.simulate
+ * (rrmpg/models/cemaneige.py:198-219) and CemaneigeGR4J.simulate (rrmpg/models/cemaneigegr4j.py:199-219).
+ * Station series prec / mean_temp / min_temp / max_temp: [T] (host or device per opts->mem).  Per-layer scalars
+ * are HOST memory in both modes and computed by the caller as the reference does (libm exp), so the outputs are
+ * bit-identical to numba: prec_factor[L] = exp((min(z_l, 4000) - z_station) * 0.0004), delta_temp[L] =
+ * (z_l - z_station) * -0.0065, flags[L] = OR of RRB_LAYER_*.  Outputs [T, L] C-order: layer precipitation,
+ * layer mean temperature, fraction of solid precipitation -- the inputs of rrb_cemaneige*_simulate. */
+#define RRB_LAYER_SCALE_PREC 1 /* multiply the station precipitation by prec_factor (else pass it through) */
+#define RRB_LAYER_SHIFT_TEMP 2 /* add delta_temp to the station temperatures (else pass them through) */
+#define RRB_LAYER_HIGH 4       /* altitude >= 1500 m: solid fraction from the mean temperature (:76-88) */
+RRB_API int rrb_snow_layers(const double* prec, const double* mean_temp, const double* min_temp, const double* max_temp,
+                            int64_t T, int64_t L, const double* prec_factor, const double* delta_temp,
+                            const int32_t* flags, double* layer_prec, double* layer_mean_temp, double* frac_solid,
+                            const rrb_opts* opts);
+
 /* ---- host-side checks of the FAST math (no GPU needed; used by the CPU test-suite) ------- */
 RRB_API void rrb_host_fast_pow(const double* x, const double* y, int64_t n, double* out);
 RRB_API void rrb_host_fast_exp2m1(const double* z, int64_t n, double* out);

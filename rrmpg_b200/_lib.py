@@ -61,6 +61,7 @@ _SIGS = {
                                        + [C.c_void_p] * 6 + [C.POINTER(Opts)]),
     "rrb_cemaneigehystgr4jice_simulate": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                                                         C.c_int64] + [C.c_void_p] * 8 + [C.POINTER(Opts)]),
+    "rrb_snow_layers": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int64] + [C.c_void_p] * 6 + [C.POINTER(Opts)]),
     "rrb_host_fast_pow": (None, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "rrb_host_fast_exp2m1": (None, [C.c_void_p, C.c_int64, C.c_void_p]),
 }
@@ -132,6 +133,8 @@ class _PinnedBlock:
 
 
 PINNED_MIN_BYTES = 1 << 20
+# include/rrmpg_b200.h: RRB_LAYER_*
+LAYER_SCALE_PREC, LAYER_SHIFT_TEMP, LAYER_HIGH = 1, 2, 4
 
 
 def host_empty(shape, dtype=np.float64):

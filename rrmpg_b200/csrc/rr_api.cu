@@ -872,6 +872,51 @@ int rrb_cemaneigehystgr4jice_simulate(const double* prec, const double* mean_tem
 }
 
 // ---- host evaluation of the FAST math (CPU test-suite) ----
+// ---- Cemaneige-family layer preprocessing ----
+int rrb_snow_layers(const double* prec, const double* mean_temp, const double* min_temp, const double* max_temp,
+                    int64_t T, int64_t L, const double* prec_factor, const double* delta_temp, const int32_t* flags,
+                    double* layer_prec, double* layer_mean_temp, double* frac_solid, const rrb_opts* opts) {
+    Prepared P;
+    int rc = prepare(opts, T, 0, nullptr, 0, &P);
+    if (rc) return rc;
+    if (!prec || !mean_temp || !min_temp || !max_temp) return fail(RRB_EINVAL, "NULL station series");
+    if (!prec_factor || !delta_temp || !flags) return fail(RRB_EINVAL, "NULL per-layer scalars");
+    if (!layer_prec || !layer_mean_temp || !frac_solid) return fail(RRB_EINVAL, "NULL output");
+    if (L < 1) return fail(RRB_EINVAL, "L = %lld", (long long)L);
+    if (L > RRB_MAX_LAYERS) return fail(RRB_EUNSUPPORTED, "L = %lld elevation layers (max %d)", (long long)L, RRB_MAX_LAYERS);
+    SnowLayerScalars k{};
+    for (int l = 0; l < (int)L; ++l) {  // the per-layer scalars are host memory in both modes
+        k.prec_factor[l] = prec_factor[l];
+        k.delta_temp[l] = delta_temp[l];
+        k.scale_prec[l] = (flags[l] & RRB_LAYER_SCALE_PREC) != 0;
+        k.shift_temp[l] = (flags[l] & RRB_LAYER_SHIFT_TEMP) != 0;
+        k.high[l] = (flags[l] & RRB_LAYER_HIGH) != 0;
+    }
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    const double *d_p, *d_me, *d_mn, *d_mx;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)T, &d_p))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)T, &d_me))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW2, min_temp, (size_t)T, &d_mn))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW3, max_temp, (size_t)T, &d_mx))) return rc;
+    const bool host = P.o.mem != RRB_MEM_DEVICE;
+    const size_t bytes = sizeof(double) * (size_t)(T * L);
+    double* outs_h[3] = {layer_prec, layer_mean_temp, frac_solid};
+    double* outs_d[3] = {layer_prec, layer_mean_temp, frac_solid};
+    if (host)
+        for (int j = 0; j < 3; ++j) {
+            void* p;
+            if ((rc = P.c->ensure(B_OUT0 + j, bytes, &p))) return rc;
+            outs_d[j] = (double*)p;
+        }
+    RRB_CUDA(launch_snow_layers(d_p, d_me, d_mn, d_mx, T, (int)L, k, outs_d[0], outs_d[1], outs_d[2], P.s));
+    if (host) {
+        for (int j = 0; j < 3; ++j)
+            RRB_CUDA(cudaMemcpyAsync(outs_h[j], outs_d[j], bytes, cudaMemcpyDeviceToHost, P.s));
+        RRB_CUDA(cudaStreamSynchronize(P.s));
+    }
+    return RRB_OK;
+}
+
 void rrb_host_fast_pow(const double* x, const double* y, int64_t n, double* out) {
     for (int64_t i = 0; i < n; ++i) out[i] = fast_pow(x[i], y[i], &h_fast_tables);
 }

@@ -74,6 +74,52 @@ cudaError_t pack_cemaneige(const double* prec, const double* mean_temp, const do
     return cudaGetLastError();
 }
 
+// ---- member-independent layer preprocessing on the device ----
+// Restates extrapolate_precipitation (rrmpg/models/cemaneige_utils.py:101-158), extrapolate_temperature (:161-208)
+// and calculate_solid_fraction (:16-98) per (timestep, layer).  The per-layer scalars (exp() altitude gradient,
+// temperature offset, which solid-fraction rule applies) are computed by the caller exactly as the reference
+// does (libm exp), everything per element is + - * / and compares: bit-identical to numba.
+__global__ void snow_layers_kernel(const double* __restrict__ prec, const double* __restrict__ mean_temp,
+                                   const double* __restrict__ min_temp, const double* __restrict__ max_temp, int64_t T,
+                                   int L, SnowLayerScalars k, double* __restrict__ layer_prec,
+                                   double* __restrict__ layer_mean, double* __restrict__ frac_solid) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= T * L) return;
+    const int64_t t = e / L;
+    const int l = (int)(e - t * L);
+    const double p = k.scale_prec[l] ? prec[t] * k.prec_factor[l] : prec[t];   // :137-147
+    const double d = k.delta_temp[l];
+    double mn = min_temp[t], me = mean_temp[t], mx = max_temp[t];
+    if (k.shift_temp[l]) {                                                      // :201-207
+        mn = mn + d;
+        me = me + d;
+        mx = mx + d;
+    }
+    double f;
+    if (!k.high[l]) {                                                           // altitude < 1500 m, :58-72
+        if (mx <= 0) f = 1;
+        else if (mn >= 0) f = 0;
+        else f = 1 - (mx / (mx - mn));
+    } else {                                                                    // :76-88
+        if (me >= 3) f = 0;
+        else if (me <= 0) f = 1;
+        else f = 1 - (me + 1) / 4;
+    }
+    layer_prec[e] = p;
+    layer_mean[e] = me;
+    frac_solid[e] = f;
+}
+
+cudaError_t launch_snow_layers(const double* prec, const double* mean_temp, const double* min_temp,
+                               const double* max_temp, int64_t T, int L, const SnowLayerScalars& k, double* layer_prec,
+                               double* layer_mean, double* frac_solid, cudaStream_t s) {
+    if (L < 1 || L > kCemaMaxLayers) return cudaErrorInvalidValue;
+    const int64_t n = T * L;
+    snow_layers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(prec, mean_temp, min_temp, max_temp, T, L, k,
+                                                                  layer_prec, layer_mean, frac_solid);
+    return cudaGetLastError();
+}
+
 int state_slots_cemaneige(int L) { return 2 * layer_class(L) + 1; }
 int state_slots_cemaneigegr4j(int L, double x4_max) {
     return 2 * layer_class(L) + cema_uh_slots(cema_uh_class(x4_max)) + 1;

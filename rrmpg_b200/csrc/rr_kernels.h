@@ -82,6 +82,18 @@ cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* 
 cudaError_t pack_cemaneige(const double* prec, const double* mean_temp, const double* frac, const double* etp,
                            int64_t T, int L, double* F, double* g_tresh, cudaStream_t s);
 
+// per-layer scalars of the Cemaneige layer preprocessing (by value: they live in the kernel parameter bank)
+struct SnowLayerScalars {
+    double prec_factor[kCemaMaxLayers];   // exp((z_l - z_station) * 0.0004), capped at 4000 m
+    double delta_temp[kCemaMaxLayers];    // (z_l - z_station) * -0.0065
+    unsigned char scale_prec[kCemaMaxLayers];  // 0: layer precipitation = station precipitation, untouched
+    unsigned char shift_temp[kCemaMaxLayers];  // 0: layer temperatures = station temperatures, untouched
+    unsigned char high[kCemaMaxLayers];        // altitude >= 1500 m: mean-temperature rule of the solid fraction
+};
+cudaError_t launch_snow_layers(const double* prec, const double* mean_temp, const double* min_temp,
+                               const double* max_temp, int64_t T, int L, const SnowLayerScalars& k, double* layer_prec,
+                               double* layer_mean, double* frac_solid, cudaStream_t s);
+
 // ---- model launches ----
 cudaError_t launch_abc(const double* F, int64_t T, double s0, const double* params, int64_t N, double* qsim,
                        double* storage, const Slab& slab, const Objective& obj, const LaunchCfg& cfg);

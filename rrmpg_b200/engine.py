@@ -379,3 +379,44 @@ def cemaneigegr4j(prec, mean_temp, etp, frac_solid, inits, params, return_storag
          _lib.ptr(prec), _lib.ptr(mean_temp), _lib.ptr(etp), _lib.ptr(frac_solid), T, L, _lib.ptr(inits),
          _lib.ptr(P), N, _lib.ptr(q), _lib.ptr(G), _lib.ptr(E), _lib.ptr(s), _lib.ptr(r), C.byref(c.opts))
     return _result(c, ["qsim", "G", "eTG", "s_store", "r_store"], [q, G, E, s, r])
+
+
+def snow_layers(prec, mean_temp, min_temp, max_temp, met_station_height, altitudes=(), device=None):
+    """Layer preprocessing of the Cemaneige family on the GPU: station series ``[T]`` -> ``(layer_prec,
+    layer_mean_temp, frac_solid)``, each ``[T, L]`` -- what ``extrapolate_precipitation``,
+    ``extrapolate_temperature`` and ``calculate_solid_fraction`` (rrmpg/models/cemaneige_utils.py:16-208) do on
+    the host, bit-identical (the per-layer ``exp`` gradient is evaluated here with libm like numba does).
+    numpy in -> numpy out, torch CUDA tensors in -> tensors out (no host round trip of the series).
+    ``altitudes`` empty: one layer at the station height, series passed through (cemaneige.py:209-217)."""
+    import math
+    alts = np.asarray(altitudes, dtype=np.float64).reshape(-1)
+    h = float(met_station_height)
+    if alts.size == 0:
+        z, flags0 = np.array([h]), 0
+    else:
+        z, flags0 = alts, _lib.LAYER_SHIFT_TEMP
+    L = z.size
+    fac, dt, fl = np.ones(L), np.zeros(L), np.zeros(L, dtype=np.int32)
+    for l in range(L):
+        f = flags0
+        if alts.size:
+            if z[l] <= 4000:                                   # cemaneige_utils.py:136-138
+                fac[l] = math.exp(float((z[l] - h) * 0.0004)); f |= _lib.LAYER_SCALE_PREC
+            elif h <= 4000:                                    # :142-144
+                fac[l] = math.exp(float((4000 - h) * 0.0004)); f |= _lib.LAYER_SCALE_PREC
+            dt[l] = (z[l] - h) * -0.0065                       # :201
+        if not (z[l] < 1500):                                  # :58
+            f |= _lib.LAYER_HIGH
+        fl[l] = f
+    c = _Call([prec, mean_temp, min_temp, max_temp], DEFAULT_MATH, device, 0, 0, None)
+    prec = c.f64(prec); mean_temp = c.f64(mean_temp, prec.shape); min_temp = c.f64(min_temp, prec.shape)
+    max_temp = c.f64(max_temp, prec.shape)
+    if prec.ndim != 1:
+        raise ValueError("station series must be one-dimensional")
+    T = prec.shape[0]
+    outs = [c.empty((T, L)) for _ in range(3)]
+    if T > 0:
+        _lib.check(_lib.lib().rrb_snow_layers(_lib.ptr(prec), _lib.ptr(mean_temp), _lib.ptr(min_temp), _lib.ptr(max_temp),
+                                              T, L, _lib.ptr(fac), _lib.ptr(dt), _lib.ptr(fl), *[_lib.ptr(o) for o in outs],
+                                              C.byref(c.opts)))
+    return tuple(outs)

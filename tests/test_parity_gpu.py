@@ -594,3 +594,30 @@ def test_full_size_hbvedu_multi_catchment_per_gpu_share():
         ref = oracle.hbvedu(temp[c], prec[c], m0[c], PE[c], TM[c], (0, 100, 3, 10), P[c, idx])
         ref_mse = ((qobs[c][:, None] - ref) ** 2).mean(axis=0)
         np.testing.assert_allclose(mse[c, idx], ref_mse, rtol=1e-9)
+
+
+def test_snow_layers_on_the_device_are_bit_identical_to_the_host_preprocessing():
+    """rrb_snow_layers = extrapolate_precipitation + extrapolate_temperature + calculate_solid_fraction on the GPU."""
+    import torch
+    from rrmpg_b200.models import _snow_inputs
+    f = synthetic.forcing(2000)
+    cases = [([550, 620, 700, 785, 920], 495), ([], 318), ([1400, 1500, 2200, 3999, 4000, 4500], 1350),
+             ([4200, 5000], 4100), ([495.0], 495)]
+    for alts, h in cases:
+        ref = _snow_inputs.to_layers(f["prec"], f["temp"], f["min_temp"], f["max_temp"], h, np.array(alts, dtype=float))
+        got = engine.snow_layers(f["prec"], f["temp"], f["min_temp"], f["max_temp"], h, alts)
+        for a, b, nm in zip(got, ref[:3], ["layer_prec", "layer_mean_temp", "frac_solid"]):
+            assert_bits_equal(a, b, f"snow_layers {alts} {nm}")
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    alts, h = cases[0]
+    got = engine.snow_layers(t(f["prec"]), t(f["temp"]), t(f["min_temp"]), t(f["max_temp"]), h, alts)
+    ref = _snow_inputs.to_layers(f["prec"], f["temp"], f["min_temp"], f["max_temp"], h, np.array(alts, dtype=float))
+    for a, b in zip(got, ref[:3]):
+        assert a.is_cuda
+        assert_bits_equal(a.cpu().numpy(), b, "snow_layers device mode")
+    # feeds the ensemble kernel without leaving the device
+    P = synthetic.random_params(CemaneigeGR4J(), 64)
+    q = engine.cemaneigegr4j(got[0], got[1], t(f["etp"]), got[2], (0, 0, 0.6, 0.7), t(engine.pack_params(P)))["qsim"]
+    qr = oracle.cemaneigegr4j(ref[0], ref[1], f["etp"], ref[2], (0, 0, 0.6, 0.7), P)
+    assert_close(q.cpu().numpy(), qr, "device preprocessing -> coupled kernel")
