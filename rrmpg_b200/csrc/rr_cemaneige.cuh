@@ -62,8 +62,13 @@ __device__ __forceinline__ double nb_max(double a, double b) { return (b > a) ? 
 
 // PLAIN = discharge only (no storages, no fused objective): the output flags are compile-time constants
 // EXACT = the run has exactly LC layers (L == LC): the per-layer bound checks fold away
+#ifdef RRB_CEMA_MINBLOCKS
+#define RRB_CEMA_BOUNDS __launch_bounds__(128, RRB_CEMA_MINBLOCKS)
+#else
+#define RRB_CEMA_BOUNDS
+#endif
 template <int LC, class Gr4j, bool FAST, bool PLAIN, bool EXACT, int FAMILY>
-__global__ void cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
+__global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, Objective obj) {
     constexpr bool COUPLED = Gr4j::kStateSlots > 0;
     constexpr bool HYST = (FAMILY & 1) != 0, ICE = (FAMILY & 2) != 0;
     constexpr int R = CemaGeom<LC>::R, TT = CemaGeom<LC>::TT;
