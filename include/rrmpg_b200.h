@@ -190,6 +190,22 @@ RRB_API int rrb_cemaneigehystgr4jice_simulate(const double* prec, const double* 
                                               double* icemelt, double* snowmelt /* nullable x7 */,
                                               const rrb_opts* opts);
 
+/* ---- catchment batches of GR4J and CemaneigeGR4J -----------------
+ * C independent catchments with N members each in one call (grid.y = catchment); the reference has no
+ * equivalent (a user loops Model.simulate over basins).  Every array gains a leading [C] axis: prec / etp
+ * [C, T], layer arrays [C, T, L], params [C, N, k], outputs [C, T, N] (G, eTG: [C, T, L, N]), opts->qobs
+ * [C, T], opts->mse [C, N].  inits (HOST memory in both modes): GR4J [C, 2] = (s_init, r_init) per catchment,
+ * CemaneigeGR4J [C, 4] = (snow_pack_init, thermal_state_init, s_init, r_init).  Results are bit-identical
+ * to C calls of the single-catchment entry points. */
+RRB_API int rrb_gr4j_simulate_multi(const double* prec, const double* etp, int64_t C, int64_t T, const double* inits,
+                                    const double* params, int64_t N, double* qsim, double* s_store,
+                                    double* r_store /* nullable x2 */, const rrb_opts* opts);
+RRB_API int rrb_cemaneigegr4j_simulate_multi(const double* prec, const double* mean_temp, const double* etp,
+                                             const double* frac_solid, int64_t C, int64_t T, int64_t L,
+                                             const double* inits, const double* params, int64_t N, double* qsim,
+                                             double* G, double* eTG, double* s_store, double* r_store /* nullable x4 */,
+                                             const rrb_opts* opts);
+
 /* ---- member-independent layer preprocessing of the Cemaneige family, on the device --------
  * Replaces extrapolate_precipitation (rrmpg/models/cemaneige_utils.py:101-158), extrapolate_temperature
  * (:161-208) and calculate_solid_fraction (:16-98), i.e. the [T] -> [T, L] step of Cemaneige.simulate

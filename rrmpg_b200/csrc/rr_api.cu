@@ -402,6 +402,95 @@ static int resolve_x4_max(Prepared* P, const double* host_or_dev_params, int64_t
 
 using namespace rrb;
 
+// ------------------------------------------------------------------------------------------------
+// Catchment batches (one launch, blockIdx.y = catchment) of the GR4J family.  Device mode: one launch over all
+// catchments into the caller's buffers.  Host mode: chunks of catchments through a two-deep device ring, the D2H
+// of chunk k overlapping the kernel of chunk k+1 (each chunk is a contiguous block of every [C, ...] output).
+// ------------------------------------------------------------------------------------------------
+struct MultiOut {
+    double* ptr;             // caller's array (host or device per opts->mem), nullable
+    int64_t per_catchment;   // elements per catchment
+};
+template <class Launch>
+static int run_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const std::vector<MultiOut>& outs, Launch&& launch) {
+    Ctx& c = *P.c;
+    const bool host = P.o.mem == RRB_MEM_HOST;
+    LaunchCfg cfg{};
+    cfg.block = P.o.block;
+    cfg.math = P.o.math;
+    cfg.sm_count = c.sm_count;
+    cfg.stream = P.s;
+    const int no = (int)outs.size();
+    std::vector<double*> ptrs(no);
+    if (!host) {
+        for (int j = 0; j < no; ++j) ptrs[j] = outs[j].ptr;
+        Objective obj{P.d_qobs, P.d_mse, T};
+        RRB_CUDA(launch(0, C, ptrs.data(), obj, cfg));
+        return RRB_OK;
+    }
+    int64_t bytes_per_catchment = 0;
+    for (const MultiOut& o : outs)
+        if (o.ptr) bytes_per_catchment += o.per_catchment * (int64_t)sizeof(double);
+    int64_t cc = C;
+    if (bytes_per_catchment > 0)
+        cc = std::max<int64_t>(1, std::min<int64_t>(C, (int64_t)(kSlabTargetBytes * 2) / bytes_per_catchment));
+    const int nchunks = (int)((C + cc - 1) / cc);
+    std::vector<double*> dev[2] = {std::vector<double*>(no, nullptr), std::vector<double*>(no, nullptr)};
+    int rc;
+    for (int sidx = 0; sidx < (nchunks > 1 ? 2 : 1); ++sidx)
+        for (int j = 0; j < no; ++j)
+            if (outs[j].ptr) {
+                void* p;
+                if ((rc = c.ensure(B_OUT0 + 2 * j + sidx, sizeof(double) * (size_t)(cc * outs[j].per_catchment), &p))) return rc;
+                dev[sidx][j] = (double*)p;
+            }
+    for (int k = 0; k < nchunks; ++k) {
+        const int sidx = k & 1;
+        const int64_t c0 = (int64_t)k * cc, c1 = std::min(C, c0 + cc);
+        if (k >= 2) RRB_CUDA(cudaStreamWaitEvent(c.compute, c.ev_free[sidx], 0));
+        Objective obj{P.d_qobs ? P.d_qobs + c0 * T : nullptr, P.d_mse ? P.d_mse + c0 * N : nullptr, T};
+        RRB_CUDA(launch(c0, c1, dev[sidx].data(), obj, cfg));
+        RRB_CUDA(cudaEventRecord(c.ev_done[sidx], c.compute));
+        RRB_CUDA(cudaStreamWaitEvent(c.copy, c.ev_done[sidx], 0));
+        for (int j = 0; j < no; ++j)
+            if (outs[j].ptr)
+                RRB_CUDA(cudaMemcpyAsync(outs[j].ptr + (size_t)(c0 * outs[j].per_catchment), dev[sidx][j],
+                                         sizeof(double) * (size_t)((c1 - c0) * outs[j].per_catchment),
+                                         cudaMemcpyDeviceToHost, c.copy));
+        RRB_CUDA(cudaEventRecord(c.ev_free[sidx], c.copy));
+    }
+    if (P.o.qobs) {
+        RRB_CUDA(cudaStreamWaitEvent(c.copy, c.ev_done[(nchunks - 1) & 1], 0));
+        RRB_CUDA(cudaMemcpyAsync(P.o.mse, P.d_mse, sizeof(double) * (size_t)(C * N), cudaMemcpyDeviceToHost, c.copy));
+    }
+    RRB_CUDA(cudaStreamSynchronize(c.copy));
+    RRB_CUDA(cudaStreamSynchronize(c.compute));
+    return RRB_OK;
+}
+
+// shared staging of a catchment batch: parameters [C][N][pwidth], per-catchment inits [C][4] (host memory in both
+// modes), observations [C][T] and the per-member objective [C][N]
+static int stage_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const double* inits4, const double** d_inits) {
+    Ctx& c = *P.c;
+    int rc;
+    void* di;
+    if ((rc = c.ensure(B_SCALAR, sizeof(double) * 4 * (size_t)C, &di))) return rc;
+    RRB_CUDA(cudaMemcpyAsync(di, inits4, sizeof(double) * 4 * (size_t)C, cudaMemcpyHostToDevice, P.s));
+    *d_inits = (const double*)di;
+    if (P.o.qobs) {
+        if ((rc = stage_in(c, P.o, B_QOBS, P.o.qobs, (size_t)(C * T), &P.d_qobs))) return rc;
+        if (P.o.mem == RRB_MEM_HOST) {
+            void* p;
+            if ((rc = c.ensure(B_MSE, sizeof(double) * (size_t)(C * N), &p))) return rc;
+            P.d_mse = (double*)p;
+        } else {
+            P.d_mse = P.o.mse;
+        }
+    }
+    return RRB_OK;
+}
+
+
 // ----------------------------------------------------------------------------------------
 // C ABI
 // ----------------------------------------------------------------------------------------
@@ -872,6 +961,95 @@ int rrb_cemaneigehystgr4jice_simulate(const double* prec, const double* mean_tem
 }
 
 // ---- host evaluation of the FAST math (CPU test-suite) ----
+int rrb_gr4j_simulate_multi(const double* prec, const double* etp, int64_t C, int64_t T, const double* inits,
+                            const double* params, int64_t N, double* qsim, double* s_store, double* r_store,
+                            const rrb_opts* opts) {
+    Prepared P;
+    int rc = prepare(opts, T, N, params, 4, &P);
+    if (rc) return rc;
+    if (C < 0) return fail(RRB_EINVAL, "C = %lld", (long long)C);
+    if (!prec || !etp || !inits) return fail(RRB_EINVAL, "NULL forcing / inits pointer");
+    if ((s_store != nullptr) != (r_store != nullptr)) return fail(RRB_EINVAL, "pass both storage outputs or none");
+    if (!qsim && !P.o.qobs && !s_store) return fail(RRB_EINVAL, "nothing to compute");
+    if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
+    if (N == 0 || C == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    const double *d_prec, *d_etp, *d_inits;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(C * T), &d_prec))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW1, etp, (size_t)(C * T), &d_etp))) return rc;
+    // the four-wide inits rows: (s_init, r_init, -, -)
+    std::vector<double> in4((size_t)C * 4, 0.0);
+    for (int64_t k = 0; k < C; ++k) { in4[4 * k] = inits[2 * k]; in4[4 * k + 1] = inits[2 * k + 1]; }
+    if ((rc = stage_in(*P.c, P.o, B_PARAMS, params, (size_t)(C * N * 4), &P.d_params))) return rc;
+    double x4_max;  // (uses the scalar scratch slot: before the inits are staged into it)
+    if ((rc = resolve_x4_max(&P, params, C * N, 4, 3, &x4_max))) return rc;
+    if (!(x4_max <= RRB_MAX_X4))
+        return fail(RRB_EUNSUPPORTED, "GR4J x4 up to %g in this batch; the unit hydrograph buffers support x4 <= %g",
+                    x4_max, RRB_MAX_X4);
+    if ((rc = stage_multi(P, C, T, N, in4.data(), &d_inits))) return rc;
+    RRB_CUDA(cudaStreamSynchronize(P.s));  // in4 is a temporary
+    const int64_t fstride = forcing_stride_flagged(T, kGr4jTT, kGr4jR);
+    void* F;
+    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)(C * fstride), &F))) return rc;
+    RRB_CUDA(pack_gr4j(d_prec, d_etp, T, (double*)F, P.s, (int)C));
+    const double* dp = P.d_params;
+    const std::vector<MultiOut> outs = {{qsim, T * N}, {s_store, T * N}, {r_store, T * N}};
+    return run_multi(P, C, T, N, outs, [=](int64_t c0, int64_t c1, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
+        Batch b{(int)(c1 - c0), fstride, T * N, d_inits + 4 * c0};
+        Slab slab{0, T, 0, nullptr, 0};
+        return launch_gr4j((const double*)F + c0 * fstride, T, 0.0, 0.0, dp + c0 * N * 4, N, x4_max, out[0], out[1], out[2],
+                           slab, ob, cfg, b);
+    });
+}
+
+int rrb_cemaneigegr4j_simulate_multi(const double* prec, const double* mean_temp, const double* etp,
+                                     const double* frac_solid, int64_t C, int64_t T, int64_t L, const double* inits,
+                                     const double* params, int64_t N, double* qsim, double* G, double* eTG,
+                                     double* s_store, double* r_store, const rrb_opts* opts) {
+    Prepared P;
+    int rc = prepare(opts, T, N, params, 6, &P);
+    if (rc) return rc;
+    if (C < 0) return fail(RRB_EINVAL, "C = %lld", (long long)C);
+    if (!prec || !mean_temp || !etp || !frac_solid || !inits) return fail(RRB_EINVAL, "NULL forcing / inits pointer");
+    if (L < 1) return fail(RRB_EINVAL, "L = %lld", (long long)L);
+    if (L > RRB_MAX_LAYERS) return fail(RRB_EUNSUPPORTED, "L = %lld elevation layers (max %d)", (long long)L, RRB_MAX_LAYERS);
+    const int nst = (G != nullptr) + (eTG != nullptr) + (s_store != nullptr) + (r_store != nullptr);
+    if (nst != 0 && nst != 4) return fail(RRB_EINVAL, "pass all four storage outputs or none");
+    if (!qsim && !P.o.qobs && nst == 0) return fail(RRB_EINVAL, "nothing to compute");
+    if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
+    if (N == 0 || C == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    const double *d_prec, *d_mt, *d_fr, *d_etp, *d_inits;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(C * T * L), &d_prec))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(C * T * L), &d_mt))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW2, frac_solid, (size_t)(C * T * L), &d_fr))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW3, etp, (size_t)(C * T), &d_etp))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_PARAMS, params, (size_t)(C * N * 6), &P.d_params))) return rc;
+    double x4_max;  // (uses the scalar scratch slot: before the inits are staged into it)
+    if ((rc = resolve_x4_max(&P, params, C * N, 6, 5, &x4_max))) return rc;
+    if (!(x4_max <= RRB_MAX_X4))
+        return fail(RRB_EUNSUPPORTED, "GR4J x4 up to %g in this batch; the unit hydrograph buffers support x4 <= %g",
+                    x4_max, RRB_MAX_X4);
+    if ((rc = stage_multi(P, C, T, N, inits, &d_inits))) return rc;
+    RRB_CUDA(cudaStreamSynchronize(P.s));  // the caller's inits array may be a temporary
+    const int LC = cema_layer_class((int)L);
+    const int64_t fstride = forcing_stride_flagged(T, cema_TT(LC), cema_R(LC));
+    void *F, *gt;
+    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)(C * fstride), &F))) return rc;
+    if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers * (size_t)C, &gt))) return rc;
+    RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, d_etp, T, (int)L, (double*)F, (double*)gt, P.s, (int)C));
+    const double* dp = P.d_params;
+    const std::vector<MultiOut> outs = {{qsim, T * N}, {G, T * L * N}, {eTG, T * L * N}, {s_store, T * N}, {r_store, T * N}};
+    const double zero4[4] = {0, 0, 0, 0};
+    return run_multi(P, C, T, N, outs, [=](int64_t c0, int64_t c1, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
+        Batch b{(int)(c1 - c0), fstride, T * N, d_inits + 4 * c0};
+        Slab slab{0, T, 0, nullptr, 0};
+        return launch_cemaneigegr4j((const double*)F + c0 * fstride, (const double*)gt + c0 * 2 * kCemaMaxLayers, T, (int)L,
+                                    zero4, dp + c0 * N * 6, N, x4_max, out[0], out[1], out[2], out[3], out[4], slab, ob,
+                                    cfg, b);
+    });
+}
+
 // ---- Cemaneige-family layer preprocessing ----
 int rrb_snow_layers(const double* prec, const double* mean_temp, const double* min_temp, const double* max_temp,
                     int64_t T, int64_t L, const double* prec_factor, const double* delta_temp, const int32_t* flags,

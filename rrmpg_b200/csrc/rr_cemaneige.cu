@@ -24,9 +24,14 @@ static int layer_class(int L) { return cema_layer_class(L); }
 __global__ void cema_pack_kernel(const double* __restrict__ prec, const double* __restrict__ mean_temp,
                                  const double* __restrict__ frac, const double* __restrict__ etp, int64_t T,
                                  int64_t Tpad, int L, int LC, int R, double* __restrict__ F,
-                                 uint32_t* __restrict__ fflag) {
+                                 uint32_t* __restrict__ fflag, int64_t fstride) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= Tpad) return;
+    const int64_t c = blockIdx.y;  // catchment
+    prec += c * T * L; mean_temp += c * T * L; frac += c * T * L;
+    if (etp) etp += c * T;
+    F += c * fstride;
+    fflag = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(fflag) + c * fstride);
     double* row = F + t * R;
     for (int k = 0; k < R; ++k) row[k] = 0.0;
     if (t < T) {
@@ -49,9 +54,12 @@ __global__ void cema_pack_kernel(const double* __restrict__ prec, const double* 
 }
 
 // one thread per layer: sequential sum in index order = numba's np.mean (cemaneige_model.py:80)
-__global__ void cema_gtresh_kernel(const double* __restrict__ F, int64_t T, int L, int R, double* __restrict__ g_tresh) {
+__global__ void cema_gtresh_kernel(const double* __restrict__ F, int64_t T, int L, int R, double* __restrict__ g_tresh,
+                                   int64_t fstride) {
     const int l = threadIdx.x;
     if (l >= L) return;
+    F += blockIdx.x * fstride;  // catchment
+    g_tresh += blockIdx.x * 2 * kCemaMaxLayers;
     double acc = 0.0;
 #pragma unroll 8
     for (int64_t t = 0; t < T; ++t) acc += F[t * R + l];
@@ -61,16 +69,18 @@ __global__ void cema_gtresh_kernel(const double* __restrict__ F, int64_t T, int 
 }
 
 cudaError_t pack_cemaneige(const double* prec, const double* mean_temp, const double* frac, const double* etp,
-                           int64_t T, int L, double* F, double* g_tresh, cudaStream_t s) {
+                           int64_t T, int L, double* F, double* g_tresh, cudaStream_t s, int count) {
     if (L < 1 || L > kCemaMaxLayers) return cudaErrorInvalidValue;
     const int LC = layer_class(L);
     const int R = cema_R(LC);
     const int64_t Tpad = padded_steps(T, cema_TT(LC));
+    const int64_t fstride = forcing_stride_flagged(T, cema_TT(LC), R);
     uint32_t* fflag = forcing_flag(F, T, cema_TT(LC), R);
-    cudaError_t e = cudaMemsetAsync(fflag, 0, kForcingFlagBytes, s);
+    cudaError_t e = cudaMemset2DAsync(fflag, sizeof(double) * (size_t)fstride, 0, kForcingFlagBytes, (size_t)count, s);
     if (e != cudaSuccess) return e;
-    cema_pack_kernel<<<(unsigned)((Tpad + 127) / 128), 128, 0, s>>>(prec, mean_temp, frac, etp, T, Tpad, L, LC, R, F, fflag);
-    cema_gtresh_kernel<<<1, 32, 0, s>>>(F, T, L, R, g_tresh);
+    cema_pack_kernel<<<dim3((unsigned)((Tpad + 127) / 128), (unsigned)count), 128, 0, s>>>(prec, mean_temp, frac, etp, T, Tpad,
+                                                                                        L, LC, R, F, fflag, fstride);
+    cema_gtresh_kernel<<<(unsigned)count, 32, 0, s>>>(F, T, L, R, g_tresh, fstride);
     return cudaGetLastError();
 }
 
@@ -131,7 +141,7 @@ cudaError_t launch_cemaneige(const double* F, const double* g_tresh, int64_t T, 
     if (N <= 0) return cudaSuccess;
     if (L < 1 || L > kCemaMaxLayers) return cudaErrorInvalidValue;
     CemaArgs a{F, g_tresh, L, T, g0, e0, 0.0, 0.0, 0.0, params, pstride, N, nullptr,
-               forcing_flag(F, T, cema_TT(layer_class(L)), cema_R(layer_class(L)))};
+               forcing_flag(F, T, cema_TT(layer_class(L)), cema_R(layer_class(L))), 1, 0, nullptr};
     CemaOut out{outflow, G, eTG, nullptr, nullptr, nullptr, nullptr, nullptr};
     switch (layer_class(L)) {
         case 1: return cema_launch_variant<1, NoGr4j, false, 0>(a, out, slab, obj, cfg);
@@ -143,9 +153,10 @@ cudaError_t launch_cemaneige(const double* F, const double* g_tresh, int64_t T, 
 cudaError_t launch_cemaneigegr4j(const double* F, const double* g_tresh, int64_t T, int L, const double* inits4,
                                  const double* params, int64_t N, double x4_max, double* qsim, double* G,
                                  double* eTG, double* s_store, double* r_store, const Slab& slab,
-                                 const Objective& obj, const LaunchCfg& cfg) {
+                                 const Objective& obj, const LaunchCfg& cfg, const Batch& batch) {
     CemaArgs a{F, g_tresh, L, T, inits4[0], inits4[1], 0.0, inits4[2], inits4[3], params, 6, N, nullptr,
-               forcing_flag(F, T, cema_TT(layer_class(L)), cema_R(layer_class(L)))};
+               forcing_flag(F, T, cema_TT(layer_class(L)), cema_R(layer_class(L))), batch.count, batch.forcing_stride,
+               batch.inits};
     CemaOut out{qsim, G, eTG, s_store, r_store, nullptr, nullptr, nullptr};
     return cema_launch_coupled<0>(a, x4_max, out, slab, obj, cfg);
 }

@@ -39,6 +39,10 @@ struct CemaArgs {
     int64_t N;
     const double* frac_ice;  // device [L], ice models only
     const uint32_t* fflag;   // forcing sanity flag written by the packer (rr_kernels.h)
+    // catchment batch (blockIdx.y = catchment): count = 1 and zero strides for the ordinary call
+    int count;
+    int64_t forcing_stride;  // doubles between the packed forcing blocks (flag slot included)
+    const double* inits_c;   // device [count][4] = (snow_pack_init, thermal_state_init, s_init, r_init), nullable
 };
 
 template <int LC>
@@ -73,6 +77,22 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
     constexpr bool HYST = (FAMILY & 1) != 0, ICE = (FAMILY & 2) != 0;
     constexpr int R = CemaGeom<LC>::R, TT = CemaGeom<LC>::TT;
     constexpr int GOFF = HYST ? 4 : 2;  // offset of x1 in the parameter record
+    if (a.count > 1) {  // blockIdx.y = catchment: shift every per-catchment pointer
+        const int64_t c = blockIdx.y;
+        const int64_t tn = a.T * a.N;
+        a.F += c * a.forcing_stride;
+        a.fflag = reinterpret_cast<const uint32_t*>(reinterpret_cast<const double*>(a.fflag) + c * a.forcing_stride);
+        a.g_tresh += c * 2 * kCemaMaxLayers;
+        a.params += c * a.N * a.pstride;
+        if (out.q) out.q += c * tn;
+        if (out.G) { out.G += c * tn * a.L; out.eTG += c * tn * a.L; }
+        if (out.s_store) { out.s_store += c * tn; out.r_store += c * tn; }
+        if (obj.qobs) { obj.qobs += c * obj.T; obj.mse += c * a.N; }
+        if (a.inits_c) {
+            a.g0 = a.inits_c[4 * c]; a.e0 = a.inits_c[4 * c + 1];
+            a.s_init = a.inits_c[4 * c + 2]; a.r_init = a.inits_c[4 * c + 3];
+        }
+    }
     const bool WRITEQ = PLAIN || out.q != nullptr, STORAGE = !PLAIN && out.G != nullptr,
                OBJ = !PLAIN && obj.qobs != nullptr;  // CTA-uniform
     const double* __restrict__ F = a.F;
@@ -386,8 +406,8 @@ template <int LC, class Gr4j, bool FAST, int FAMILY>
 static cudaError_t cema_launch_variant(const CemaArgs& a, const CemaOut& out, const Slab& slab, const Objective& obj,
                                        const LaunchCfg& cfg) {
     constexpr int R = CemaGeom<LC>::R, TT = CemaGeom<LC>::TT;
-    const int block = cfg.block > 0 ? cfg.block : pick_block(a.N, cfg.sm_count, 128);
-    const unsigned grid = (unsigned)((a.N + block - 1) / block);
+    const int block = cfg.block > 0 ? cfg.block : pick_block(a.N * a.count, cfg.sm_count, a.N >= 128 ? 128 : 64);
+    const dim3 grid((unsigned)((a.N + block - 1) / block), (unsigned)a.count);
     const size_t smem = forcing_smem_bytes<R, TT>() + ((FAMILY & 1) ? 0 : 32 * LC) +
                         ((FAST && Gr4j::kStateSlots > 0) ? fastmath_smem_bytes() : 0);
     const bool plain = out.q && !out.G && !obj.qobs;

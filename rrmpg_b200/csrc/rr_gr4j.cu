@@ -11,9 +11,12 @@
 namespace rrb {
 
 __global__ void gr4j_pack_kernel(const double* __restrict__ prec, const double* __restrict__ etp, int64_t T,
-                                 int64_t Tpad, double* __restrict__ F, uint32_t* __restrict__ fflag) {
+                                 int64_t Tpad, double* __restrict__ F, uint32_t* __restrict__ fflag, int64_t fstride) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= Tpad) return;
+    const int64_t c = blockIdx.y;  // catchment
+    prec += c * T; etp += c * T; F += c * fstride;
+    fflag = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(fflag) + c * fstride);
     double2 v = make_double2(0.0, 0.0);
     if (t < T) {
         v.x = prec[t];
@@ -23,12 +26,14 @@ __global__ void gr4j_pack_kernel(const double* __restrict__ prec, const double* 
     reinterpret_cast<double2*>(F)[t] = v;
 }
 
-cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* F, cudaStream_t s) {
+cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* F, cudaStream_t s, int count) {
     int64_t Tpad = padded_steps(T, kGr4jTT);
+    const int64_t fstride = forcing_stride_flagged(T, kGr4jTT, kGr4jR);
     uint32_t* fflag = forcing_flag(F, T, kGr4jTT, kGr4jR);
-    cudaError_t e = cudaMemsetAsync(fflag, 0, kForcingFlagBytes, s);
+    cudaError_t e = cudaMemset2DAsync(fflag, sizeof(double) * (size_t)fstride, 0, kForcingFlagBytes, (size_t)count, s);
     if (e != cudaSuccess) return e;
-    gr4j_pack_kernel<<<(unsigned)((Tpad + 255) / 256), 256, 0, s>>>(prec, etp, T, Tpad, F, fflag);
+    gr4j_pack_kernel<<<dim3((unsigned)((Tpad + 255) / 256), (unsigned)count), 256, 0, s>>>(prec, etp, T, Tpad, F, fflag,
+                                                                                        fstride);
     return cudaGetLastError();
 }
 
@@ -47,7 +52,17 @@ template <class Member, bool FAST, bool PLAIN>
 __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double r_init,
                             const double* __restrict__ params, int64_t N, double* __restrict__ qsim,
                             double* __restrict__ s_store, double* __restrict__ r_store, Slab slab,
-                            Objective obj, const uint32_t* __restrict__ fflag) {
+                            Objective obj, const uint32_t* __restrict__ fflag, Batch batch) {
+    if (batch.count > 1) {  // blockIdx.y = catchment: shift every per-catchment pointer
+        const int64_t c = blockIdx.y;
+        F += c * batch.forcing_stride;
+        fflag = reinterpret_cast<const uint32_t*>(reinterpret_cast<const double*>(fflag) + c * batch.forcing_stride);
+        params += c * N * 4;
+        if (qsim) qsim += c * batch.out_stride;
+        if (s_store) { s_store += c * batch.out_stride; r_store += c * batch.out_stride; }
+        if (obj.qobs) { obj.qobs += c * obj.T; obj.mse += c * N; }
+        if (batch.inits) { s_init = batch.inits[4 * c]; r_init = batch.inits[4 * c + 1]; }
+    }
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     // threads past the end of the ensemble recompute member N-1 and store the same values to the same
     // addresses: no predicate lives in the time loop
@@ -144,26 +159,26 @@ int state_slots_gr4j(double x4_max) {
 template <class Member, bool FAST>
 static cudaError_t launch_variant(const double* F, int64_t T, double s_init, double r_init, const double* params, int64_t N,
                                   double* qsim, double* s_store, double* r_store, const Slab& slab,
-                                  const Objective& obj, const LaunchCfg& cfg) {
-    const int block = cfg.block > 0 ? cfg.block : pick_block(N, cfg.sm_count, 128);
-    const unsigned grid = (unsigned)((N + block - 1) / block);
+                                  const Objective& obj, const LaunchCfg& cfg, const Batch& batch) {
+    const int block = cfg.block > 0 ? cfg.block : pick_block(N * batch.count, cfg.sm_count, N >= 128 ? 128 : 64);
+    const dim3 grid((unsigned)((N + block - 1) / block), (unsigned)batch.count);
     const size_t smem = forcing_smem_bytes<kGr4jR, kGr4jTT>() + (FAST ? fastmath_smem_bytes() : 0);
     const uint32_t* fflag = forcing_flag(F, T, kGr4jTT, kGr4jR);
     if (qsim && !s_store && !obj.qobs)
         gr4j_kernel<Member, FAST, true><<<grid, block, smem, cfg.stream>>>(F, s_init, r_init, params, N, qsim, s_store,
-                                                                           r_store, slab, obj, fflag);
+                                                                           r_store, slab, obj, fflag, batch);
     else
         gr4j_kernel<Member, FAST, false><<<grid, block, smem, cfg.stream>>>(F, s_init, r_init, params, N, qsim, s_store,
-                                                                            r_store, slab, obj, fflag);
+                                                                            r_store, slab, obj, fflag, batch);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gr4j(const double* F, int64_t T, double s_init, double r_init, const double* params,
                         int64_t N, double x4_max, double* qsim, double* s_store, double* r_store,
-                        const Slab& slab, const Objective& obj, const LaunchCfg& cfg) {
-    if (N <= 0) return cudaSuccess;
+                        const Slab& slab, const Objective& obj, const LaunchCfg& cfg, const Batch& batch) {
+    if (N <= 0 || batch.count <= 0) return cudaSuccess;
     const bool fast = cfg.math == RRB_MATH_FAST_;
-#define RRB_GO(M_, F_) return launch_variant<M_, F_>(F, T, s_init, r_init, params, N, qsim, s_store, r_store, slab, obj, cfg)
+#define RRB_GO(M_, F_) return launch_variant<M_, F_>(F, T, s_init, r_init, params, N, qsim, s_store, r_store, slab, obj, cfg, batch)
     switch (uh_class(x4_max)) {
         case 0:
             if (fast) RRB_GO(Gr4jUh3F, true);

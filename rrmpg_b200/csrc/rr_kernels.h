@@ -23,9 +23,10 @@ struct Slab {
 // strides describe the ordinary single-catchment call.
 struct Batch {
     int count;
-    int64_t forcing_stride;  // packed forcing: Tpad * R
+    int64_t forcing_stride;  // packed forcing: Tpad * R (GR4J / Cemaneige family: + the flag slot, forcing_stride_flagged)
     int64_t out_stride;      // every [T, N] output: T * N
-    const double* inits;     // optional device array [count][4] of per-catchment initial states (nullable)
+    const double* inits;     // optional device array [count][4] of per-catchment initial states (nullable);
+                             // GR4J: (s_init, r_init, -, -), CemaneigeGR4J: (snow_pack, thermal_state, s_init, r_init)
 };
 
 struct LaunchCfg {
@@ -70,6 +71,10 @@ template <class D>
 inline uint32_t* forcing_flag(D* F, int64_t T, int TT, int R) {
     return reinterpret_cast<uint32_t*>(const_cast<double*>(F) + padded_steps(T, TT) * R);
 }
+// catchment batches of these models: every catchment's block is followed by its own flag slot
+inline int64_t forcing_stride_flagged(int64_t T, int TT, int R) {
+    return padded_steps(T, TT) * R + (int64_t)(kForcingFlagBytes / sizeof(double));
+}
 
 // ---- forcing packers (device pointers in, packed F[Tpad][R] out) ----
 cudaError_t pack_abc(const double* prec, int64_t T, double* F, cudaStream_t s);
@@ -77,10 +82,12 @@ cudaError_t pack_abc(const double* prec, int64_t T, double* F, cudaStream_t s);
 // (non-zero: a precipitation value is not finite -- the FAST kernel then leaves the launch to the PRECISE one)
 cudaError_t pack_hbvedu(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
                         const double* T_m, int64_t T, double* F, int math, int count, cudaStream_t s);
-cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* F, cudaStream_t s);
+// count catchments: prec, etp [count][T]; F [count][forcing_stride_flagged]
+cudaError_t pack_gr4j(const double* prec, const double* etp, int64_t T, double* F, cudaStream_t s, int count = 1);
 // writes F and g_tresh[L] (sequential np.mean semantics, rrmpg/models/cemaneige_model.py:80)
+// count catchments: layer arrays [count][T][L], etp [count][T]; F [count][forcing_stride_flagged], g_tresh [count][32]
 cudaError_t pack_cemaneige(const double* prec, const double* mean_temp, const double* frac, const double* etp,
-                           int64_t T, int L, double* F, double* g_tresh, cudaStream_t s);
+                           int64_t T, int L, double* F, double* g_tresh, cudaStream_t s, int count = 1);
 
 // per-layer scalars of the Cemaneige layer preprocessing (by value: they live in the kernel parameter bank)
 struct SnowLayerScalars {
@@ -106,7 +113,8 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
 // uh_cap: 0 = derive from x4_max
 cudaError_t launch_gr4j(const double* F, int64_t T, double s_init, double r_init, const double* params,
                         int64_t N, double x4_max, double* qsim, double* s_store, double* r_store,
-                        const Slab& slab, const Objective& obj, const LaunchCfg& cfg);
+                        const Slab& slab, const Objective& obj, const LaunchCfg& cfg,
+                        const Batch& batch = Batch{1, 0, 0, nullptr});
 
 cudaError_t launch_cemaneige(const double* F, const double* g_tresh, int64_t T, int L, double g0, double e0,
                              const double* params, int64_t pstride, int64_t N, double* outflow, double* G,
@@ -115,7 +123,8 @@ cudaError_t launch_cemaneige(const double* F, const double* g_tresh, int64_t T, 
 cudaError_t launch_cemaneigegr4j(const double* F, const double* g_tresh, int64_t T, int L, const double* inits4,
                                  const double* params, int64_t N, double x4_max, double* qsim, double* G,
                                  double* eTG, double* s_store, double* r_store, const Slab& slab,
-                                 const Objective& obj, const LaunchCfg& cfg);
+                                 const Objective& obj, const LaunchCfg& cfg,
+                                 const Batch& batch = Batch{1, 0, 0, nullptr});
 
 // snow-ice family: family bit 0 = hysteresis snow routine, bit 1 = ice melt.  inits5 = (snow_pack_init,
 // thermal_state_init, sca_init, s_init, r_init); outputs nullable (all storages of the family or none).

@@ -381,6 +381,85 @@ def cemaneigegr4j(prec, mean_temp, etp, frac_solid, inits, params, return_storag
     return _result(c, ["qsim", "G", "eTG", "s_store", "r_store"], [q, G, E, s, r])
 
 
+def _multi_common(c, params, width, qobs, Cc, T):
+    P = c.f64(params)
+    if P.ndim != 3 or P.shape[2] != width or P.shape[0] != Cc:
+        raise ValueError(f"params must be [C, N, {width}] with one block per catchment")
+    N = P.shape[1]
+    if qobs is not None:
+        q_ = c.f64(qobs, (Cc, T))
+        c.opts.qobs = _lib.ptr(q_)
+        c.mse = c.empty((Cc, N))
+        c.opts.mse = _lib.ptr(c.mse)
+    return P, N
+
+
+def _records_to_matrix(params):
+    if not _is_torch(params):
+        params = np.asarray(params)
+        if params.dtype.names:
+            Cn, Nn = params.shape
+            params = pack_params(params.reshape(-1)).reshape(Cn, Nn, -1)
+    return params
+
+
+def gr4j_multi(prec, etp, inits, params, return_storage=False, qobs=None, want_qsim=True, math=DEFAULT_MATH,
+               device=None, block=0, out=None, x4_max=0.0):
+    """GR4J for C independent catchments with N members each, one launch.
+
+    prec, etp: [C, T]; inits: (2,) or [C, 2] = (s_init, r_init); params: [C, N, 4] (or a [C, N] record array);
+    qobs: [C, T].  Returns {'qsim': [C, T, N], 's_store', 'r_store', 'mse': [C, N]}; bit-identical to looping
+    ``gr4j`` over the catchments."""
+    params = _records_to_matrix(params)
+    c = _Call([prec, etp, params], math, device, block, 0, None, x4_max)
+    prec = c.f64(prec); etp = c.f64(etp, prec.shape)
+    if prec.ndim != 2:
+        raise ValueError("expected prec / etp [C, T]")
+    Cc, T = prec.shape
+    P, N = _multi_common(c, params, 4, qobs, Cc, T)
+    ini = np.ascontiguousarray(np.broadcast_to(np.asarray(inits, dtype=np.float64).reshape(-1, 2), (Cc, 2)))
+    c.keep.append(ini)
+    out = out or {}
+    q = c.empty((Cc, T, N), out.get("qsim")) if want_qsim else None
+    st = [c.empty((Cc, T, N), out.get(n)) for n in ("s_store", "r_store")] if return_storage else [None, None]
+    if Cc > 0 and T > 0 and N > 0:
+        _lib.check(_lib.lib().rrb_gr4j_simulate_multi(_lib.ptr(prec), _lib.ptr(etp), Cc, T, _lib.ptr(ini), _lib.ptr(P), N,
+                                                      _lib.ptr(q), _lib.ptr(st[0]), _lib.ptr(st[1]), C.byref(c.opts)))
+    return _result(c, ["qsim", "s_store", "r_store"], [q] + st)
+
+
+def cemaneigegr4j_multi(prec, mean_temp, etp, frac_solid, inits, params, return_storages=False, qobs=None,
+                        want_qsim=True, math=DEFAULT_MATH, device=None, block=0, out=None, x4_max=0.0):
+    """Cemaneige + GR4J for C independent catchments with N members each, one launch.
+
+    prec, mean_temp, frac_solid: [C, T, L] layer arrays (``snow_layers`` per catchment); etp: [C, T];
+    inits: (4,) or [C, 4] = (snow_pack_init, thermal_state_init, s_init, r_init); params: [C, N, 6].
+    Returns {'qsim': [C, T, N], 'G', 'eTG': [C, T, L, N], 's_store', 'r_store', 'mse': [C, N]}; bit-identical to
+    looping ``cemaneigegr4j`` over the catchments."""
+    params = _records_to_matrix(params)
+    c = _Call([prec, mean_temp, etp, frac_solid, params], math, device, block, 0, None, x4_max)
+    prec = c.f64(prec); mean_temp = c.f64(mean_temp, prec.shape); frac_solid = c.f64(frac_solid, prec.shape)
+    if prec.ndim != 3:
+        raise ValueError("layer arrays must be [C, T, L]")
+    Cc, T, L = prec.shape
+    etp = c.f64(etp, (Cc, T))
+    P, N = _multi_common(c, params, 6, qobs, Cc, T)
+    ini = np.ascontiguousarray(np.broadcast_to(np.asarray(inits, dtype=np.float64).reshape(-1, 4), (Cc, 4)))
+    c.keep.append(ini)
+    out = out or {}
+    q = c.empty((Cc, T, N), out.get("qsim")) if want_qsim else None
+    if return_storages:
+        G, E = c.empty((Cc, T, L, N), out.get("G")), c.empty((Cc, T, L, N), out.get("eTG"))
+        s, r = c.empty((Cc, T, N), out.get("s_store")), c.empty((Cc, T, N), out.get("r_store"))
+    else:
+        G = E = s = r = None
+    if Cc > 0 and T > 0 and N > 0:
+        _lib.check(_lib.lib().rrb_cemaneigegr4j_simulate_multi(
+            _lib.ptr(prec), _lib.ptr(mean_temp), _lib.ptr(etp), _lib.ptr(frac_solid), Cc, T, L, _lib.ptr(ini), _lib.ptr(P),
+            N, _lib.ptr(q), _lib.ptr(G), _lib.ptr(E), _lib.ptr(s), _lib.ptr(r), C.byref(c.opts)))
+    return _result(c, ["qsim", "G", "eTG", "s_store", "r_store"], [q, G, E, s, r])
+
+
 def snow_layers(prec, mean_temp, min_temp, max_temp, met_station_height, altitudes=(), device=None):
     """Layer preprocessing of the Cemaneige family on the GPU: station series ``[T]`` -> ``(layer_prec,
     layer_mean_temp, frac_solid)``, each ``[T, L]`` -- what ``extrapolate_precipitation``,

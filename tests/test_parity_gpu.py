@@ -621,3 +621,50 @@ def test_snow_layers_on_the_device_are_bit_identical_to_the_host_preprocessing()
     q = engine.cemaneigegr4j(got[0], got[1], t(f["etp"]), got[2], (0, 0, 0.6, 0.7), t(engine.pack_params(P)))["qsim"]
     qr = oracle.cemaneigegr4j(ref[0], ref[1], f["etp"], ref[2], (0, 0, 0.6, 0.7), P)
     assert_close(q.cpu().numpy(), qr, "device preprocessing -> coupled kernel")
+
+
+def test_gr4j_family_multi_catchment_equals_a_loop_over_catchments():
+    """rrb_gr4j_simulate_multi / rrb_cemaneigegr4j_simulate_multi: grid.y = catchment, bit-identical to one call per
+    catchment (host mode incl. the chunked D2H ring, device mode with the fused objective only)."""
+    import torch
+    from rrmpg_b200.models import _snow_inputs
+    Cn, T, N = 4, 500, 90
+    fs = [synthetic.forcing(T, seed=300 + c) for c in range(Cn)]
+    prec = np.stack([f["prec"] for f in fs]); etp = np.stack([f["etp"] * (1 + 0.05 * c) for c, f in enumerate(fs)])
+    qobs = np.abs(np.random.default_rng(5).normal(1.0, 0.5, (Cn, T)))
+    # ---- GR4J
+    P = np.stack([engine.pack_params(synthetic.random_params(GR4J(), N, seed=400 + c)) for c in range(Cn)])
+    P[2, 5, 0] = 1e-6   # one catchment has a CTA outside the FAST contract: per-catchment fallback
+    inits = np.array([[0.6, 0.7], [0.1, 0.9], [0.0, 0.0], [1.0, 0.3]])
+    multi = engine.gr4j_multi(prec, etp, inits, P, return_storage=True, qobs=qobs)
+    assert multi["qsim"].shape == (Cn, T, N) and multi["mse"].shape == (Cn, N)
+    for c in range(Cn):
+        one = engine.gr4j(prec[c], etp[c], inits[c, 0], inits[c, 1], P[c], return_storage=True, qobs=qobs[c])
+        for nm in one:
+            assert_bits_equal(multi[nm][c], one[nm], f"gr4j catchment {c} {nm}")
+        assert_close(multi["qsim"][c], oracle.gr4j(prec[c], etp[c], inits[c, 0], inits[c, 1], P[c]), f"gr4j catchment {c}")
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    r = engine.gr4j_multi(t(prec), t(etp), inits, t(P), qobs=t(qobs), want_qsim=False)
+    torch.cuda.synchronize()
+    assert set(r) == {"mse"}
+    assert_bits_equal(r["mse"].cpu().numpy(), multi["mse"], "gr4j device-mode objective")
+    # ---- CemaneigeGR4J, catchments at different station heights, one without rain -> G_tresh = 0
+    alts = [550, 620, 700, 785, 920]
+    lay = [_snow_inputs.to_layers(f["prec"] * (c != 1), f["temp"] - 2 * c, f["min_temp"] - 2 * c, f["max_temp"] - 2 * c,
+                                  400 + 50 * c, np.array(alts, dtype=float)) for c, f in enumerate(fs)]
+    lp = np.stack([l[0] for l in lay]); lt = np.stack([l[1] for l in lay]); fr = np.stack([l[2] for l in lay])
+    PC = np.stack([engine.pack_params(synthetic.random_params(CemaneigeGR4J(), N, seed=500 + c)) for c in range(Cn)])
+    ini4 = np.array([[0, 0, 0.6, 0.7], [5.0, -1.0, 0.5, 0.5], [0, 0, 0.2, 0.9], [20.0, 0.0, 0.6, 0.7]])
+    multi = engine.cemaneigegr4j_multi(lp, lt, etp, fr, ini4, PC, return_storages=True, qobs=qobs)
+    assert multi["G"].shape == (Cn, T, 5, N)
+    for c in range(Cn):
+        one = engine.cemaneigegr4j(lp[c], lt[c], etp[c], fr[c], ini4[c], PC[c], return_storages=True, qobs=qobs[c])
+        for nm in one:
+            assert_bits_equal(multi[nm][c], one[nm], f"cemaneigegr4j catchment {c} {nm}")
+        ref = oracle.cemaneigegr4j(lp[c], lt[c], etp[c], fr[c], ini4[c], PC[c], return_storages=True)
+        assert_bits_equal(multi["G"][c], ref[1], f"cemaneigegr4j catchment {c} G vs oracle")
+        assert_close(multi["qsim"][c], ref[0], f"cemaneigegr4j catchment {c} qsim vs oracle")
+    r = engine.cemaneigegr4j_multi(t(lp), t(lt), t(etp), t(fr), ini4, t(PC), qobs=t(qobs), want_qsim=False)
+    torch.cuda.synchronize()
+    assert_bits_equal(r["mse"].cpu().numpy(), multi["mse"], "cemaneigegr4j device-mode objective")
