@@ -668,3 +668,74 @@ def test_gr4j_family_multi_catchment_equals_a_loop_over_catchments():
     r = engine.cemaneigegr4j_multi(t(lp), t(lt), t(etp), t(fr), ini4, t(PC), qobs=t(qobs), want_qsim=False)
     torch.cuda.synchronize()
     assert_bits_equal(r["mse"].cpu().numpy(), multi["mse"], "cemaneigegr4j device-mode objective")
+
+
+def test_randomized_parity_sweep_all_models():
+    """Seeded random problem shapes (series length, ensemble size, launch geometry, initial states, parameter draws up
+    to the edges of the default bounds) for every model, FAST math, against the oracle."""
+    from rrmpg_b200.models import _snow_inputs
+    rng = np.random.default_rng(20261017)
+    worst = {}
+
+    def note(name, got, ref):
+        got, ref = np.asarray(got), np.asarray(ref)
+        assert_close(got, ref, name)
+        m = np.isfinite(ref) & (np.abs(ref) > 1e-6)
+        if m.any():
+            worst[name] = max(worst.get(name, 0.0), float(np.max(np.abs(got[m] - ref[m]) / np.abs(ref[m]))))
+
+    def edge(P, frac=0.15):
+        """push a fraction of the members onto the lower / upper bound of one random field each"""
+        P = P.copy()
+        names = P.dtype.names
+        for i in rng.choice(P.shape[0], max(1, int(frac * P.shape[0])), replace=False):
+            nm = names[rng.integers(len(names))]
+            lo, hi = P[nm].min(), P[nm].max()
+            P[nm][i] = lo if rng.random() < 0.5 else hi
+        return P
+
+    for trial in range(6):
+        T = int(rng.integers(3, 900))
+        N = int(rng.integers(1, 700))
+        block = int(rng.choice([0, 32, 64, 128, 256]))
+        f = synthetic.forcing(T, seed=int(rng.integers(1 << 30)))
+        m0 = (f["month"] - 1).astype(np.int8)
+        # HBVEdu
+        P = edge(synthetic.random_params(HBVEdu(), N, seed=int(rng.integers(1 << 30))))
+        ini = (float(rng.uniform(0, 50)), float(rng.uniform(20, 200)), float(rng.uniform(0, 20)), float(rng.uniform(0, 30)))
+        got = engine.hbvedu(f["temp"], f["prec"], m0, f["PE_m"], f["T_m"], ini, P, return_storage=True, block=block)
+        ref = oracle.hbvedu(f["temp"], f["prec"], m0, f["PE_m"], f["T_m"], ini, P, return_storage=True)
+        for nm, r in zip(["qsim", "snow", "soil", "s1", "s2"], ref):
+            note("hbvedu." + nm, got[nm], r)
+        # ABC (bit-exact)
+        Pa = synthetic.random_params(ABCModel(), N, seed=int(rng.integers(1 << 30)))
+        s0 = float(rng.uniform(0, 10))
+        assert_bits_equal(engine.abc(f["prec"], s0, Pa, block=block)["qsim"], oracle.abc(f["prec"], s0, Pa), "abc")
+        # GR4J
+        Pg = edge(synthetic.random_params(GR4J(), N, seed=int(rng.integers(1 << 30))))
+        si, ri = float(rng.uniform(0, 1)), float(rng.uniform(0, 1))
+        got = engine.gr4j(f["prec"], f["etp"], si, ri, Pg, return_storage=True, block=block)
+        ref = oracle.gr4j(f["prec"], f["etp"], si, ri, Pg, return_storage=True)
+        for nm, r in zip(["qsim", "s_store", "r_store"], ref):
+            note("gr4j." + nm, got[nm], r)
+        # Cemaneige (bit-exact) and CemaneigeGR4J, random number of layers
+        L = int(rng.integers(1, 8))
+        alts = sorted(float(a) for a in rng.uniform(300, 2500, L))
+        lp, lt, fr, _ = _snow_inputs.to_layers(f["prec"], f["temp"], f["min_temp"], f["max_temp"], 480.0, np.array(alts))
+        Pc = edge(synthetic.random_params(Cemaneige(), N, seed=int(rng.integers(1 << 30))))
+        g0, e0 = float(rng.uniform(0, 40)), float(-rng.uniform(0, 3))
+        got = engine.cemaneige(lp, lt, fr, g0, e0, Pc, return_storages=True, block=block)
+        ref = oracle.cemaneige(lp, lt, fr, g0, e0, Pc, return_storages=True)
+        for nm, r in zip(["outflow", "G", "eTG"], ref):
+            assert_bits_equal(got[nm], r, f"cemaneige L={L} {nm}")
+        Pcg = edge(synthetic.random_params(CemaneigeGR4J(), N, seed=int(rng.integers(1 << 30))))
+        ini4 = (g0, e0, si, ri)
+        got = engine.cemaneigegr4j(lp, lt, f["etp"], fr, ini4, Pcg, return_storages=True, block=block)
+        ref = oracle.cemaneigegr4j(lp, lt, f["etp"], fr, ini4, Pcg, return_storages=True)
+        assert_bits_equal(got["G"], ref[1], f"cemaneigegr4j L={L} G")
+        assert_bits_equal(got["eTG"], ref[2], f"cemaneigegr4j L={L} eTG")
+        for nm, r in zip(["qsim", "s_store", "r_store"], [ref[0], ref[3], ref[4]]):
+            note("cemaneigegr4j." + nm, got[nm], r)
+    print("\nworst relative deviation from the oracle (|ref| > 1e-6), FAST math: "
+          + ", ".join(f"{k} {v:.1e}" for k, v in sorted(worst.items())))
+    assert max(worst.values()) < 1e-10
