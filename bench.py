@@ -40,6 +40,11 @@ CPU_SAMPLE_MEMBERS = 16384
 # kernels of ours per device-mode step: forcing pack + ensemble kernel (+ in FAST mode the PRECISE kernel queued
 # behind it as the fallback for non-finite rain, which exits at once on this workload)
 LAUNCHES_PER_STEP = {"fast": 3, "precise": 2}
+# The binding roof of the HBV kernel is instruction issue, not HBM: per member-timestep it
+# executes 61.6 warp-instructions of which ~33 are fp64 (ncu, profiles/r01_ncu_full_hbv_v8_summary.txt), an fp64 warp
+# instruction holds a sub-partition's issue port for 2 cycles (16 fp64 lanes), every other one for 1.
+HBV_FAST_WARP_INSTR, HBV_FAST_FP64_INSTR = 61.6, 33.0
+SM_COUNT, SUBPARTITIONS = 148, 4
 
 
 def measured_peaks():
@@ -288,13 +293,26 @@ def main():
                 "note": "algorithmic bytes = 8 B x members x timesteps per launch; duration = CUDA-event time of one "
                         "step (forcing pack kernel + ensemble kernel + the idle fallback launch; pack and fallback "
                         "are <0.3% of it, see profiles/ launch list)"}
+    issue = None
+    if args.math == "fast":
+        slots = 2 * HBV_FAST_FP64_INSTR + (HBV_FAST_WARP_INSTR - HBV_FAST_FP64_INSTR)
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        ceiling = SM_COUNT * SUBPARTITIONS * mhz * 1e6 * 32 / slots
+        warps = (hi - lo + 31) // 32
+        per_sp = warps / (SM_COUNT * SUBPARTITIONS)
+        issue = {"bound": "issue (fp64 = 2 slots)", "issue_slots_per_member_step": slots,
+                 "ceiling_member_steps_per_s": ceiling, "achieved": (hi - lo) * T_STEPS / (kernel_ms * 1e-3),
+                 "frac": (hi - lo) * T_STEPS / (kernel_ms * 1e-3) / ceiling,
+                 "load_balance_limit": per_sp / float(int(per_sp) + (per_sp > int(per_sp))),
+                 "note": "second roofline, explains the HBM fraction: instruction counts from the committed ncu capture; "
+                         "load_balance_limit = mean / max warps per SM sub-partition for this ensemble size"}
     cpu = None
     if world == 1 and not args.no_cpu:
         cpu, _ = cpu_baseline_run(f, P)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_dict(world), "roofline": roofline,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP[args.math] * args.steps, "clocks": clocks,
+            "issue_roofline": issue, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP[args.math] * args.steps, "clocks": clocks,
             "parity_spot_check": parity}
     line["config"]["math"] = args.math
     line["config"]["members_per_gpu"] = members

@@ -417,7 +417,9 @@ static cudaError_t cema_launch_variant(const CemaArgs& a, const CemaOut& out, co
         else if (a.L == LC) RRB_CEMA(false, true);
         else RRB_CEMA(false, false);
     } else {
-        RRB_CEMA(false, false);  // the snow-ice family keeps one general variant per configuration
+        // the snow-ice family: the discharge-only / exact-layer-count specialisation plus one general variant
+        if (plain && a.L == LC) RRB_CEMA(true, true);
+        else RRB_CEMA(false, false);
     }
 #undef RRB_CEMA
     return cudaGetLastError();

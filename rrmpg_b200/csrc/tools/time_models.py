@@ -48,3 +48,14 @@ out2 = {"outflow": buf}
 report("Cemaneige L=5", timeit(lambda: engine.cemaneige(lp, lt, fr, 0.0, 0.0, P, out=out2, math=math)))
 P = t(engine.pack_params(synthetic.random_params(CemaneigeGR4J(), N)))
 report("CemaneigeGR4J L=5", timeit(lambda: engine.cemaneigegr4j(lp, lt, etp, fr, (0, 0, 0.6, 0.7), P, out=out, math=math, x4_max=2.9)))
+# snow-ice couplings
+from rrmpg_b200.models import CemaneigeGR4JIce, CemaneigeHystGR4J, CemaneigeHystGR4JIce
+fice = t(np.full(L, 0.1))
+for name, cls, hyst, ice in (("CemaneigeGR4JIce", CemaneigeGR4JIce, False, True), ("CemaneigeHystGR4J", CemaneigeHystGR4J, True, False),
+                             ("CemaneigeHystGR4JIce", CemaneigeHystGR4JIce, True, True)):
+    Pm = synthetic.random_params(cls(), N)
+    x4 = float(np.max(Pm["x4"]))
+    P = t(engine.pack_params(Pm))
+    ini = (0, 0, 0, 0.6, 0.7) if hyst else (0, 0, 0.6, 0.7)
+    report(f"{name} L=5 x4<={x4:.1f}", timeit(lambda: engine.snowice_gr4j(hyst, ice, lp, lt, etp, fice if ice else None, fr, ini, P,
+                                                                       out=out, math=math, x4_max=x4)))
