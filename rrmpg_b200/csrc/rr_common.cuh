@@ -75,9 +75,6 @@ __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 // Written as setp + selp so they cost one DSETP and two SELs; the C++ ternary is pattern-matched by
 // the compiler into a DSETP.MAX + NaN fix-up sequence of six instructions.
 __device__ __forceinline__ double nb_max0(double x) {
-#ifdef RRB_X_NOMAXASM
-    return (x > 0.0) ? x : 0.0;
-#endif
     double r;
     asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, 0d0000000000000000;\n\t"
         "selp.f64 %0, %1, 0d0000000000000000, p;\n\t}"
@@ -86,9 +83,6 @@ __device__ __forceinline__ double nb_max0(double x) {
     return r;
 }
 __device__ __forceinline__ double nb_min(double a, double b) {
-#ifdef RRB_X_NOMAXASM
-    return (b < a) ? b : a;
-#endif
     double r;
     asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %2, %1;\n\tselp.f64 %0, %2, %1, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
     return r;

@@ -210,8 +210,8 @@ constexpr int kHbvGroup = RRB_HBV_GROUP;
 // Cost model (measured, profiles/r01_*): with one thread per member the 65 536-member workload leaves 3.5
 // warps per SM sub-partition and the kernel is ISSUE bound -- every fp64 instruction holds the issue port
 // for 2 cycles (16 fp64 lanes per sub-partition), every other instruction for 1.  The body below is written
-// to minimise (2 x fp64 + other) instructions per member-timestep: ~22 fp64 + ~25 other without the pow,
-// ~27 fp64 + ~15 other more with it.
+// to minimise (2 x fp64 + other) instructions per member-timestep: ~21 fp64 + ~22 other without the pow,
+// ~27 fp64 + ~11 other more with it (61.6 warp-instructions on average on the bench forcing, ncu).
 template <bool WRITEQ, bool STORAGE, bool OBJ>
 __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                                 const double* __restrict__ params, int64_t N, HbvOut out, Slab slab,
@@ -312,13 +312,7 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
                 const double s2_new = fma(s1, K_p, s2 * c2);                         // :121-123
                 double s1_new = fma(s1, c1, -oK);                                    // :114-118 without prec_eff
                 double soil_new = (soil + liquid[g]) - ea;                           // :111 without prec_eff
-#if defined(RRB_EXP_NOPOW)
-                if (false) {
-#elif defined(RRB_EXP_ALWAYSPOW)
-                if (true) {
-#else
                 if (need[g]) {
-#endif
                     double pw = fast_pow_unchecked_smem(soil * inv_FC, Beta, tb, pr);
                     if (!safe) pw = hbv_slow_pow(soil, FC, Beta);
                     const double prec_eff = liquid[g] * pw;

@@ -132,22 +132,6 @@ __host__ __device__ __forceinline__ double fast_pow(double x, double y, const Fa
 }
 
 #ifdef __CUDACC__
-// polynomial coefficients in the constant bank: DFMA takes a c[bank][offset] operand directly, so
-// no registers and no per-step immediate moves are spent on them
-static __constant__ double kc_log2_poly[7] = RRB_LOG2_POLY;
-static __constant__ double kc_exp2_poly[6] = RRB_EXP2_POLY;
-
-// polynomial coefficients as a kernel parameter: they then live in the parameter constant bank and
-// DFMA reads them as c[0x0][offset] operands -- no registers, no LDC / MOV instructions in the loop
-struct PowCoef {
-    double A[7];  // log2(1+r) = r (A0 + A1 r + ... )
-    double C[6];  // 2^r - 1   = r (C0 + C1 r + ... )
-};
-inline PowCoef make_pow_coef() {
-    PowCoef c = {RRB_LOG2_POLY, RRB_EXP2_POLY};
-    return c;
-}
-
 // Device-side variants reading the tables through a 32-bit shared-window address (see lds_f64x2 in
 // rr_common.cuh for why).  No range checks: the caller guarantees 2^-16 < x < 2^16 and |y| < 32,
 // hence x positive normal and |y log2 x| <= 512.  Out-of-contract operands give garbage, never a fault
@@ -212,84 +196,6 @@ __device__ __forceinline__ PowRegs load_pow_regs(uint32_t tb_addr) {
                    lds_f64_at(c + 32)};
 }
 
-// 2^z - 1 for z >= 0 through the shared-memory tables (device twin of fast_exp2m1_nonneg)
-__device__ __forceinline__ double fast_exp2m1_nonneg_smem(double z, uint32_t tb_addr) {
-    constexpr double C[6] = RRB_EXP2_POLY;
-    constexpr double kShift = 0x1.8p52 / tables::kExpN;
-    z = (z > 64.0) ? 64.0 : z;
-    double kd = z + kShift;
-    const uint32_t ki = (uint32_t)__double2loint(kd);
-    kd -= kShift;
-    const double r = z - kd;
-    const uint32_t j8 = (ki & (tables::kExpN - 1)) * 8u;
-    uint32_t tlo, thi;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
-                 : "=r"(tlo), "=r"(thi)
-                 : "r"(tb_addr + (uint32_t)offsetof(FastTables, exp2tab) + j8));
-    const double scale = __hiloint2double((int)(thi + (ki << 13)), (int)tlo);
-    double m1;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(m1) : "r"(tb_addr + (uint32_t)offsetof(FastTables, exp2m1tab) + j8));
-    const double base = (ki < (uint32_t)tables::kExpN) ? m1 : scale - 1.0;
-    const double r2 = r * r;
-    const double a = fma(r, C[1], C[0]);
-    double b = fma(r, C[3], C[2]);
-    b = fma(r2, C[4], b);
-    const double t = fma(r2, b, a);
-    return fma(scale, r * t, base);
-}
-
-// num / den for a normal, positive, comfortably ranged den (here den in [2, ~4]): reciprocal seed
-// refined by two Newton steps and one residual correction -- correctly rounded in practice, no
-// special-case branches (the IEEE division sequence carries a slow-path call)
-__device__ __forceinline__ double fast_div_pos(double num, double den) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
-    double e = fma(-den, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-den, y, 1.0);
-    y = fma(y, e, y);
-    const double q = num * y;
-    const double r = fma(-den, q, num);
-    return fma(r, y, q);
-}
-
-// v^(-1/4) for finite v >= 1, used for the (1 + u^4)^(-0.25) terms of rrmpg/models/gr4j_model.py:117,145.
-// Seed from the fp64 reciprocal-square-root unit applied twice (rsq(v) * rsq(rsq(v)) = v^-1/2 * v^1/4),
-// one third-order and one Newton refinement: within ~1 ulp, no conversions, no special-case branch.
-// Non-finite / NaN operands take libm.
-__device__ __forceinline__ double rsqrt_approx_f64(double a) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    return y;
-}
-__device__ __forceinline__ double fast_rsqrt4_ge1(double v) {
-    if (!(v < 1e300)) return pow(v, -0.25);  // inf / nan: keep libm semantics
-    const double a = rsqrt_approx_f64(v);
-    double y = a * rsqrt_approx_f64(a);               // ~2^-19 relative
-    double y2 = y * y;
-    double e = fma(-v, y2 * y2, 1.0);                 // 1 - v y^4
-    y = fma(y, e * fma(e, 0.15625, 0.25), y);         // y (1 + e/4 + 5 e^2/32): error ~ e^3
-    y2 = y * y;
-    e = fma(-v, y2 * y2, 1.0);
-    return fma(y * 0.25, e, y);
-}
-
-// w^3.5 for w >= 0 (NaN for w < 0, like pow): w^4 * w^(-1/2), the reciprocal square root from the seed unit
-// plus two Newton steps.  w == 0 and non-finite w go through exact selects.
-__device__ __forceinline__ double fast_pow35_nonneg(double w) {
-    double y = rsqrt_approx_f64(w);
-    double t = w * y;
-    double e = fma(-t, y, 1.0);        // 1 - w y^2
-    y = fma(0.5 * y, e, y);
-    t = w * y;
-    e = fma(-t, y, 1.0);
-    y = fma(0.5 * y, e, y);
-    const double w2 = w * w;
-    const double r = (w2 * w2) * y;
-    // w = 0 -> 0 (the seed is inf there); w = inf -> inf; w < 0 or NaN -> NaN comes out of the seed
-    return (w == 0.0) ? 0.0 : ((w > 1e300) ? w : r);
-}
-
 // ----------------------------------------------------------------------------------------
 // Branch-free variants for SANE operands (finite, moderately ranged; the kernels establish that once
 // per CTA before the time loop -- Gr4jMember::sane -- and run the reference-order arithmetic otherwise).
@@ -298,6 +204,11 @@ __device__ __forceinline__ double fast_pow35_nonneg(double w) {
 // issue slots.  Seeds come from MUFU.RCP64H / MUFU.RSQ64H (~2^-20 relative); one third-order
 // correction takes them below 2 ulp.
 // ----------------------------------------------------------------------------------------
+__device__ __forceinline__ double rsqrt_approx_f64(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    return y;
+}
 struct Exp2Regs {
     double c0, c1, c2, c3, c4;  // (2^r - 1)/r, degree 4
     double k5_32, k3_8;         // 5/32, 3/8: multiplier constants of the third-order corrections (an FMA takes one immediate)

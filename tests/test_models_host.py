@@ -228,3 +228,19 @@ def test_member_blocks_partition_the_ensemble():
         assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
         sizes = [b - a for a, b in blocks]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_multi_catchment_argument_checks_fail_before_the_library_is_touched():
+    z = np.zeros
+    with pytest.raises(ValueError, match=r"\[C, N, 4\]"):
+        engine.gr4j_multi(z((2, 10)), z((2, 10)), (0.5, 0.5), z((3, 5, 4)))          # one params block per catchment
+    with pytest.raises(ValueError, match=r"\[C, N, 4\]"):
+        engine.gr4j_multi(z((2, 10)), z((2, 10)), (0.5, 0.5), z((2, 5, 6)))          # GR4J records have 4 fields
+    with pytest.raises(ValueError):
+        engine.gr4j_multi(z((2, 10)), z((2, 11)), (0.5, 0.5), z((2, 5, 4)))          # etp length
+    with pytest.raises(ValueError, match=r"\[C, T, L\]"):
+        engine.cemaneigegr4j_multi(z((2, 10)), z((2, 10)), z((2, 10)), z((2, 10)), (0, 0, .5, .5), z((2, 5, 6)))
+    with pytest.raises(ValueError):
+        engine.cemaneigegr4j_multi(z((2, 10, 3)), z((2, 10, 3)), z((2, 9)), z((2, 10, 3)), (0, 0, .5, .5), z((2, 5, 6)))
+    with pytest.raises(ValueError):
+        engine.snow_layers(z((4, 2)), z((4, 2)), z((4, 2)), z((4, 2)), 300.0, [400.0])  # station series are 1-D
