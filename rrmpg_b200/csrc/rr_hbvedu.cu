@@ -40,7 +40,8 @@ __global__ void hbv_pack_kernel(const double* __restrict__ temp, const double* _
         v.z = temp[t] - T_m[m];
         v.w = PE_m[m];
         if (fast) v.z = v.z * v.w;
-        if (!(fabs(v.y) <= 1e300)) atomicOr(fflag, 1u);  // inf / NaN precipitation: FAST contract broken
+        // inf / NaN precipitation or temperature: FAST contract broken (prec - prec, sign test of temp - T_t)
+        if (!(fabs(v.y) <= 1e300) || !(fabs(v.x) <= 1e300)) atomicOr(fflag, 1u);
     }
     reinterpret_cast<double4*>(F)[t] = v;
 }
@@ -216,7 +217,8 @@ template <bool WRITEQ, bool STORAGE, bool OBJ>
 __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                                 const double* __restrict__ params, int64_t N, HbvOut out, Slab slab,
                                 Objective obj, Batch batch, const uint32_t* __restrict__ fflag) {
-    // FAST contract: finite precipitation (the snow routine below forms prec - prec for "no liquid water").  The
+    // FAST contract: finite precipitation and temperature (the snow routine below forms prec - prec for "no liquid
+    // water" and reads temp < T_t off the sign of temp - T_t).  The
     // packer flags anything else and the PRECISE kernel launched right behind this one takes the whole launch.
     if (*fflag != 0u) return;
     HBV_BATCH_PROLOGUE
@@ -226,6 +228,8 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
     const double T_t = p[0], DD = p[1], FC = p[2], Beta = p[3], C = p[4], PWP = p[5];
     const double K_0 = p[6], K_1 = p[7], K_2 = p[8], K_p = p[9], L = p[10];
     double inv_FC = 1.0 / FC, inv_PWP = 1.0 / PWP;
+    // max(0, s1 - L) is read off the sign bit below; numba's max(0, NaN) = 0 for a NaN threshold = an infinite one
+    const double Lq = (L == L) ? L : __longlong_as_double(0x7FF0000000000000LL);
     double c1 = 1.0 - K_1 - K_p;  // s1 (1 - K_1 - K_p)
     double c2 = 1.0 - K_2;        // s2 (1 - K_2)
     // The table-driven pow is used when soil/FC is within [2^-15, 2^15) and |Beta| < 32 (then
@@ -289,9 +293,10 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
                 // melt = min(snow, DD (temp - T_t)) serves both max(0, snow - m) = snow - melt and the liquid water
                 // prec + melt; the cold branch (snow + prec, no liquid water) is the same two additions with
                 // -prec in place of melt: snow - (-prec) and prec + (-prec) = +0 for finite precipitation
-                const double m = DD * (f[g].temp - T_t);
+                const double dtt = f[g].temp - T_t;
+                const double m = DD * dtt;
                 const double melt = (m < snow) ? m : snow;
-                const bool cold = f[g].temp < T_t;
+                const bool cold = __double2hiint(dtt) < 0;  // temp < T_t through the sign of the (finite) difference
                 const double nprec = __hiloint2double(__double2hiint(f[g].prec) ^ (int)0x80000000, __double2loint(f[g].prec));
                 const double sel = cold ? nprec : melt;
                 snow = snow - sel;
@@ -302,13 +307,14 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
             // ---- prec_eff = liquid * (soil/FC)^Beta (:99) is +0 whenever liquid == 0 and the power is
             // finite, so a warp evaluates the pow only if one of its members has liquid water
 #pragma unroll
-            for (int g = 0; g < G; ++g) need[g] = __any_sync(0xffffffffu, liquid[g] != 0.0);
+            for (int g = 0; g < G; ++g)  // liquid != 0 on the bit pattern (one LOP3; -0 and NaN count as water)
+                need[g] = __any_sync(0xffffffffu, (__double2hiint(liquid[g]) | __double2loint(liquid[g])) != 0);
             // ---- B: soil moisture, response routine, discharge
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 const bool safe = ((uint32_t)__double2hiint(soil) - safe_lo) < safe_span;
                 const double ea = (soil > PWP) ? pe[g] : pe[g] * (soil * inv_PWP);  // :105-108
-                const double oK = nb_max0(s1 - L) * K_0;
+                const double oK = max0_sane(s1 - Lq) * K_0;  // sign-bit select: a NaN s1 poisons s1_new and q either way
                 const double s2_new = fma(s1, K_p, s2 * c2);                         // :121-123
                 double s1_new = fma(s1, c1, -oK);                                    // :114-118 without prec_eff
                 double soil_new = (soil + liquid[g]) - ea;                           // :111 without prec_eff
