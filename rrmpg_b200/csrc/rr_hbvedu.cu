@@ -230,6 +230,9 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
     double inv_FC = 1.0 / FC, inv_PWP = 1.0 / PWP;
     // max(0, s1 - L) is read off the sign bit below; numba's max(0, NaN) = 0 for a NaN threshold = an infinite one
     const double Lq = (L == L) ? L : __longlong_as_double(0x7FF0000000000000LL);
+    // temp < T_t is read off the sign of temp - T_t: a NaN threshold of either sign means "never cold", like the
+    // reference's comparison (the subtraction then yields the canonical, positive NaN)
+    const double Tt = (T_t == T_t) ? T_t : __longlong_as_double(0x7FF8000000000000LL);
     double c1 = 1.0 - K_1 - K_p;  // s1 (1 - K_1 - K_p)
     double c2 = 1.0 - K_2;        // s2 (1 - K_2)
     // The table-driven pow is used when soil/FC is within [2^-15, 2^15) and |Beta| < 32 (then
@@ -293,7 +296,7 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
                 // melt = min(snow, DD (temp - T_t)) serves both max(0, snow - m) = snow - melt and the liquid water
                 // prec + melt; the cold branch (snow + prec, no liquid water) is the same two additions with
                 // -prec in place of melt: snow - (-prec) and prec + (-prec) = +0 for finite precipitation
-                const double dtt = f[g].temp - T_t;
+                const double dtt = f[g].temp - Tt;
                 const double m = DD * dtt;
                 const double melt = (m < snow) ? m : snow;
                 const bool cold = __double2hiint(dtt) < 0;  // temp < T_t through the sign of the (finite) difference

@@ -242,6 +242,10 @@ def test_nan_propagation_matches_oracle():
     P = synthetic.random_params(HBVEdu(), 40)
     P["FC"][3] = -150.0   # negative base of the pow -> NaN from the first wet step on
     P["Beta"][7] = np.nan
+    P["T_t"][11] = np.copysign(np.nan, -1.0)   # a NaN threshold (either sign) is never "cold" in the reference
+    P["T_t"][12] = np.nan
+    P["L"][13] = np.nan                        # max(0, s1 - NaN) = 0 in numba
+    P["DD"][14] = np.nan
     prec = f["prec"].copy()
     q = engine.hbvedu(f["temp"], prec, f["month"] - 1, f["PE_m"], f["T_m"], (0, 100, 3, 10), P)["qsim"]
     ref = oracle.hbvedu(f["temp"], prec, f["month"] - 1, f["PE_m"], f["T_m"], (0, 100, 3, 10), P)
