@@ -53,19 +53,37 @@ __global__ void cema_pack_kernel(const double* __restrict__ prec, const double* 
     }
 }
 
-// one thread per layer: sequential sum in index order = numba's np.mean (cemaneige_model.py:80)
+// G_tresh needs numba's np.mean = a sequential sum in index order (cemaneige_model.py:80), one chain of T
+// dependent additions per layer.  The chain itself is short (8 cycles per addition); what would dominate is the
+// latency of T strided global loads, so the whole CTA stages tiles of the snow columns in shared memory and
+// thread l < L walks its column there.  One CTA per catchment.
+constexpr int kGtTile = 256;  // timesteps per staged tile (32 KB of static shared memory at 16 layers)
 __global__ void cema_gtresh_kernel(const double* __restrict__ F, int64_t T, int L, int R, double* __restrict__ g_tresh,
                                    int64_t fstride) {
-    const int l = threadIdx.x;
-    if (l >= L) return;
+    __shared__ double tile[kGtTile * kCemaMaxLayers];
     F += blockIdx.x * fstride;  // catchment
     g_tresh += blockIdx.x * 2 * kCemaMaxLayers;
     double acc = 0.0;
+    for (int64_t t0 = 0; t0 < T; t0 += kGtTile) {
+        const int nt = (int)((T - t0 < kGtTile) ? (T - t0) : kGtTile);
+        for (int e = threadIdx.x; e < nt * L; e += blockDim.x) {
+            const int k = e / L, l = e - k * L;
+            tile[e] = F[(t0 + k) * R + l];
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < L) {
+            const int l = threadIdx.x;
 #pragma unroll 8
-    for (int64_t t = 0; t < T; ++t) acc += F[t * R + l];
-    const double mean = acc / (double)T;
-    g_tresh[l] = 0.9 * 365.25 * mean;                 // cemaneige_model.py:80
-    g_tresh[kCemaMaxLayers + l] = 365.25 * mean;      // Psolannual, cemaneigehyst_model.py:102
+            for (int k = 0; k < nt; ++k) acc += tile[k * L + l];
+        }
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < L) {
+        const int l = threadIdx.x;
+        const double mean = acc / (double)T;
+        g_tresh[l] = 0.9 * 365.25 * mean;                 // cemaneige_model.py:80
+        g_tresh[kCemaMaxLayers + l] = 365.25 * mean;      // Psolannual, cemaneigehyst_model.py:102
+    }
 }
 
 cudaError_t pack_cemaneige(const double* prec, const double* mean_temp, const double* frac, const double* etp,
@@ -80,7 +98,7 @@ cudaError_t pack_cemaneige(const double* prec, const double* mean_temp, const do
     if (e != cudaSuccess) return e;
     cema_pack_kernel<<<dim3((unsigned)((Tpad + 127) / 128), (unsigned)count), 128, 0, s>>>(prec, mean_temp, frac, etp, T, Tpad,
                                                                                         L, LC, R, F, fflag, fstride);
-    cema_gtresh_kernel<<<(unsigned)count, 32, 0, s>>>(F, T, L, R, g_tresh, fstride);
+    cema_gtresh_kernel<<<(unsigned)count, 256, 0, s>>>(F, T, L, R, g_tresh, fstride);
     return cudaGetLastError();
 }
 

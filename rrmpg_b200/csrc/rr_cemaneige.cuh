@@ -77,32 +77,26 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
     constexpr bool HYST = (FAMILY & 1) != 0, ICE = (FAMILY & 2) != 0;
     constexpr int R = CemaGeom<LC>::R, TT = CemaGeom<LC>::TT;
     constexpr int GOFF = HYST ? 4 : 2;  // offset of x1 in the parameter record
-    if (a.count > 1) {  // blockIdx.y = catchment: shift every per-catchment pointer
-        const int64_t c = blockIdx.y;
-        const int64_t tn = a.T * a.N;
-        a.F += c * a.forcing_stride;
-        a.fflag = reinterpret_cast<const uint32_t*>(reinterpret_cast<const double*>(a.fflag) + c * a.forcing_stride);
-        a.g_tresh += c * 2 * kCemaMaxLayers;
-        a.params += c * a.N * a.pstride;
-        if (out.q) out.q += c * tn;
-        if (out.G) { out.G += c * tn * a.L; out.eTG += c * tn * a.L; }
-        if (out.s_store) { out.s_store += c * tn; out.r_store += c * tn; }
-        if (obj.qobs) { obj.qobs += c * obj.T; obj.mse += c * a.N; }
-        if (a.inits_c) {
-            a.g0 = a.inits_c[4 * c]; a.e0 = a.inits_c[4 * c + 1];
-            a.s_init = a.inits_c[4 * c + 2]; a.r_init = a.inits_c[4 * c + 3];
-        }
-    }
+    // blockIdx.y = catchment (0 for the ordinary call): every per-catchment pointer below is shifted by cb blocks
+    const int64_t cb = (a.count > 1) ? (int64_t)blockIdx.y : 0;
     const bool WRITEQ = PLAIN || out.q != nullptr, STORAGE = !PLAIN && out.G != nullptr,
                OBJ = !PLAIN && obj.qobs != nullptr;  // CTA-uniform
-    const double* __restrict__ F = a.F;
+    const double* __restrict__ F = a.F + cb * a.forcing_stride;
+    const uint32_t* __restrict__ fflag =
+        reinterpret_cast<const uint32_t*>(reinterpret_cast<const double*>(a.fflag) + cb * a.forcing_stride);
+    const double* __restrict__ g_tresh = a.g_tresh + cb * 2 * kCemaMaxLayers;
+    double g0 = a.g0, e0 = a.e0, s_init = a.s_init, r_init = a.r_init;
+    if (a.inits_c) {
+        g0 = a.inits_c[4 * cb]; e0 = a.inits_c[4 * cb + 1];
+        s_init = a.inits_c[4 * cb + 2]; r_init = a.inits_c[4 * cb + 3];
+    }
     const int64_t N = a.N;
     int L = a.L;
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     // threads past the end of the ensemble recompute member N-1 and store the same values to the same
     // addresses: no predicate lives in the time loop
     const int64_t i = gi < N ? gi : N - 1;
-    const double* p = a.params + a.pstride * i;
+    const double* p = a.params + a.pstride * (cb * N + i);
     // record = (CTG, Kf[, Thacc, Rsp][, x1, x2, x3, x4][, DDF]) -- cemaneige.py:64-65, cemaneigegr4j.py:67-72,
     // cemaneigegr4jice.py:73-79, cemaneigehystgr4j.py:72-79, cemaneigehystgr4jice.py:78-86
     const double CTG = p[0], Kf = p[1];
@@ -121,14 +115,14 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
             // sca[t-1] at t = 0 is sca[T-1], still 0 from np.zeros -- or sca_init itself when T == 1 (:126)
             sca_prev[l] = (a.T == 1) ? a.sca0 : 0.0;
             swe_max[l] = 0.0;
-            thmelt[l] = ((l < L) ? a.g_tresh[kCemaMaxLayers + l] : 0.0) * Rsp;  // Psolannual * Rsp, :139
+            thmelt[l] = ((l < L) ? g_tresh[kCemaMaxLayers + l] : 0.0) * Rsp;  // Psolannual * Rsp, :139
         }
         if (ICE) fice[l] = (l < L) ? a.frac_ice[l] : 0.0;
     }
     double inv_thacc = 1.0 / Thacc;
     const uint32_t thacc_span = HYST ? div_invariant_span(Thacc) : 0u;
     Gr4j gr;
-    if constexpr (COUPLED) gr.init(p + GOFF, a.s_init, a.r_init);
+    if constexpr (COUPLED) gr.init(p + GOFF, s_init, r_init);
     double acc = 0.0;
     constexpr int kLayerSlots = HYST ? 4 : 2;
     constexpr int kSlots = kLayerSlots * LC + Gr4j::kStateSlots;
@@ -147,8 +141,8 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
     }
     int64_t stride = N, strideL = (int64_t)L * N;
     pin(stride); pin(strideL);
-    const int64_t off = i + (slab.t_begin - slab.row0) * N;
-    const int64_t offL = i + (slab.t_begin - slab.row0) * L * N;  // [rows, L, N] storages
+    const int64_t off = i + (slab.t_begin - slab.row0) * N + cb * a.T * N;
+    const int64_t offL = i + (slab.t_begin - slab.row0) * L * N + cb * a.T * N * L;  // [rows, L, N] storages
     double* q_o = WRITEQ ? out.q + off : nullptr;
     double* s_o = (COUPLED && STORAGE) ? out.s_store + off : nullptr;
     double* r_o = (COUPLED && STORAGE) ? out.r_store + off : nullptr;
@@ -157,6 +151,7 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
     double* S_o = (HYST && STORAGE) ? out.sca + offL : nullptr;
     double* im_o = (ICE && STORAGE) ? out.icemelt + off : nullptr;
     double* sm_o = (FAMILY == 3 && STORAGE) ? out.snowmelt + off : nullptr;
+    const double* __restrict__ qobs_c = OBJ ? obj.qobs + cb * obj.T : nullptr;
     const double layers = (double)L;
     double inv_layers = 1.0 / layers;
     pin(inv_layers);
@@ -169,7 +164,7 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
         double* rec = reinterpret_cast<double*>(rrb_smem + forcing_smem_bytes<R, TT>());
         if ((int)threadIdx.x < LC) {
             const int l = threadIdx.x;
-            const double gt = (l < L) ? a.g_tresh[l] : 0.0;
+            const double gt = (l < L) ? g_tresh[l] : 0.0;
             rec[4 * l] = gt;
             rec[4 * l + 1] = 1.0 / gt;
             reinterpret_cast<uint32_t*>(rec + 4 * l + 2)[0] = div_invariant_span(gt);
@@ -189,8 +184,8 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
     // layers.  Any other CTA runs the general step.
     bool snow_ok = false;
     if constexpr (!HYST) {
-        snow_ok = Kf >= 0.0 && Kf <= 1e6 && fabs(CTG) <= 1e6 && a.g0 >= 0.0 && a.g0 <= 1e6 && fabs(a.e0) <= 1e6 &&
-                  *a.fflag == 0u;
+        snow_ok = Kf >= 0.0 && Kf <= 1e6 && fabs(CTG) <= 1e6 && g0 >= 0.0 && g0 <= 1e6 && fabs(e0) <= 1e6 &&
+                  *fflag == 0u;
 #pragma unroll
         for (int l = 0; l < LC; ++l) {
             if (l < L) {
@@ -210,7 +205,7 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
         // FAST path contract of Gr4jMember: finite, moderately ranged parameters, initial states and forcing --
         // then the snow routine feeds GR4J finite water.  CTA-uniform; the barrier also publishes the tables
         // (the peeled first step below already reads them).
-        bool sane = gr.sane && *a.fflag == 0u && fabs(a.g0) <= 1e6 && fabs(a.e0) <= 1e6 && fabs(a.sca0) <= 1e6 &&
+        bool sane = gr.sane && *fflag == 0u && fabs(g0) <= 1e6 && fabs(e0) <= 1e6 && fabs(a.sca0) <= 1e6 &&
                     (HYST || snow_ok);
         for (int k = 0; k < (int)a.pstride; ++k) sane = sane && fabs(p[k]) <= 1e6;
         if (ICE) {
@@ -236,8 +231,8 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
         for (int l = 0; l < LC; ++l) {
             if (EXACT || l < L) {
                 const double snow = f[l], rain = f[LC + l], Tm = f[2 * LC + l];
-                double g = FIRST ? a.g0 : G[l] + snow;                    // :85-88
-                double e = FIRST ? a.e0 : CTG * eTG[l] + omCTG * Tm;      // :91-94
+                double g = FIRST ? g0 : G[l] + snow;                    // :85-88
+                double e = FIRST ? e0 : CTG * eTG[l] + omCTG * Tm;      // :91-94
                 e = (e > 0) ? 0.0 : e;                                    // :95-96
                 double melt;
                 if constexpr (!HYST && CONTRACT) {
@@ -340,7 +335,7 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
             }
         }
         if (OBJ) {
-            const double d = obj.qobs[t] - qv;
+            const double d = qobs_c[t] - qv;
             acc += d * d;
         }
     };
@@ -382,7 +377,7 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
             if constexpr (COUPLED) gr.save(slab.state + (int64_t)kLayerSlots * LC * N, N, i);
             if (OBJ) slab.state[(int64_t)kSlots * N + i] = acc;
         }
-        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i] = acc / (double)obj.T;
+        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[cb * N + i] = acc / (double)obj.T;
     }
 }
 
