@@ -41,9 +41,9 @@ CPU_SAMPLE_MEMBERS = 16384
 # behind it as the fallback for non-finite rain, which exits at once on this workload)
 LAUNCHES_PER_STEP = {"fast": 3, "precise": 2}
 # The binding roof of the HBV kernel is instruction issue, not HBM: per member-timestep it
-# executes 61.6 warp-instructions of which ~33 are fp64 (ncu, profiles/r01_ncu_full_hbv_v8_summary.txt), an fp64 warp
+# executes 61.6 warp-instructions of which ~30 are fp64 (ncu, profiles/r01_ncu_full_hbv_v9_summary.txt), an fp64 warp
 # instruction holds a sub-partition's issue port for 2 cycles (16 fp64 lanes), every other one for 1.
-HBV_FAST_WARP_INSTR, HBV_FAST_FP64_INSTR = 61.6, 33.0
+HBV_FAST_WARP_INSTR, HBV_FAST_FP64_INSTR = 61.6, 30.0
 SM_COUNT, SUBPARTITIONS = 148, 4
 
 
