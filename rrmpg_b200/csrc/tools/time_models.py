@@ -37,6 +37,12 @@ report("ABC", timeit(lambda: engine.abc(prec, 0.0, P, out=out, math=math)))
 P = t(engine.pack_params(synthetic.random_params(HBVEdu(), N)))
 temp, month0, pe, tm = t(f["temp"]), t(f["month"] - 1, torch.int8), t(f["PE_m"]), t(f["T_m"])
 report("HBVEdu", timeit(lambda: engine.hbvedu(temp, prec, month0, pe, tm, (0, 100, 3, 10), P, out=out, math=math)))
+if N <= 131072:  # all five outputs: 40 B per member-step, 38 GB at 65 536 members
+    st = {k: torch.empty((T, N), dtype=torch.float64, device=dev) for k in ("snow", "soil", "s1", "s2")}
+    st["qsim"] = buf
+    report("HBVEdu + 4 storages (40 B)", timeit(lambda: engine.hbvedu(temp, prec, month0, pe, tm, (0, 100, 3, 10), P, return_storage=True,
+                                                                  out=st, math=math)), nbytes=40)
+    del st
 P = t(engine.pack_params(synthetic.random_params(GR4J(), N)))
 etp = t(f["etp"])
 report("GR4J", timeit(lambda: engine.gr4j(prec, etp, 0.6, 0.7, P, out=out, math=math, x4_max=2.9)))
