@@ -24,6 +24,15 @@ elif model in ("cemaneige", "cemaneigegr4j"):
     else:
         P = t(engine.pack_params(synthetic.random_params(CemaneigeGR4J(), N)))
         fn = lambda: engine.cemaneigegr4j(lp, lt, etp, fr, (0, 0, 0.6, 0.7), P, out={"qsim": buf}, math=math, x4_max=2.9)
+elif model == "hyst":
+    from rrmpg_b200.models import CemaneigeHystGR4J
+    lp, lt, fr, L = _snow_inputs.to_layers(f["prec"], f["temp"], f["min_temp"], f["max_temp"], synthetic.MET_STATION_HEIGHT,
+                                           np.array(synthetic.ALTITUDES))
+    lp, lt, fr = t(lp), t(lt), t(fr)
+    Pm = synthetic.random_params(CemaneigeHystGR4J(), N)
+    P = t(engine.pack_params(Pm))
+    fn = lambda: engine.snowice_gr4j(True, False, lp, lt, etp, None, fr, (0, 0, 0, 0.6, 0.7), P, out={"qsim": buf}, math=math,
+                                     x4_max=float(Pm["x4"].max()))
 elif model == "abc":
     P = t(engine.pack_params(synthetic.random_params(ABCModel(), N)))
     fn = lambda: engine.abc(prec, 0.0, P, out={"qsim": buf}, math=math)

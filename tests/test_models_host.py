@@ -244,3 +244,25 @@ def test_multi_catchment_argument_checks_fail_before_the_library_is_touched():
         engine.cemaneigegr4j_multi(z((2, 10, 3)), z((2, 10, 3)), z((2, 9)), z((2, 10, 3)), (0, 0, .5, .5), z((2, 5, 6)))
     with pytest.raises(ValueError):
         engine.snow_layers(z((4, 2)), z((4, 2)), z((4, 2)), z((4, 2)), 300.0, [400.0])  # station series are 1-D
+
+
+def test_vectorised_fit_driver_polishes_with_batched_gradients():
+    """models/_fit.py: one loss call per DE generation ((k, S) trial matrix) and one per L-BFGS-B gradient
+    ((k, k + 1) matrix) -- checked on a numpy objective, no GPU involved."""
+    from rrmpg_b200.models import _fit
+    target = np.array([0.3, -1.2, 2.5])
+    shapes = []
+
+    def loss(X, scale):
+        X = np.asarray(X, dtype=np.float64)
+        shapes.append(X.shape)
+        P = _fit.as_population(X)                       # [S, k]
+        return _fit.finish(scale * ((P - target) ** 2).sum(axis=1) + 1.0, X)
+
+    bounds = [(-3.0, 3.0)] * 3
+    res = _fit.minimise(loss, bounds, (2.0,), de_kwargs=dict(seed=3, maxiter=30, tol=1e-3))
+    assert np.allclose(res.x, target, atol=1e-6) and abs(res.fun - 1.0) < 1e-10
+    assert all(len(s) == 2 for s in shapes)             # never a scalar trial vector: every call is a batch
+    assert (3, 4) in shapes                             # the polish step: k + 1 members per gradient
+    rough = _fit.minimise(loss, bounds, (2.0,), de_kwargs=dict(seed=3, maxiter=30, tol=1e-3, polish=False))
+    assert res.fun <= rough.fun and res.nfev > rough.nfev
