@@ -21,6 +21,7 @@ struct CemaGeom {
 
 struct NoGr4j {
     static constexpr int kStateSlots = 0;
+    static constexpr size_t kOrdSmemBytes = 0;
 };
 
 struct CemaOut {
@@ -121,8 +122,11 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
     }
     double inv_thacc = 1.0 / Thacc;
     const uint32_t thacc_span = HYST ? div_invariant_span(Thacc) : 0u;
+    extern __shared__ __align__(128) unsigned char rrb_smem[];
+    // dynamic shared memory = [forcing ring | G_tresh records | FAST tables | unit hydrograph ordinates (long class)]
+    constexpr size_t kOrdOff = forcing_smem_bytes<R, TT>() + (HYST ? 0 : 32 * LC) + ((COUPLED && FAST) ? fastmath_smem_bytes() : 0);
     Gr4j gr;
-    if constexpr (COUPLED) gr.init(p + GOFF, s_init, r_init);
+    if constexpr (COUPLED) gr.init(p + GOFF, s_init, r_init, smem_u32(rrb_smem + kOrdOff));
     double acc = 0.0;
     constexpr int kLayerSlots = HYST ? 4 : 2;
     constexpr int kSlots = kLayerSlots * LC + Gr4j::kStateSlots;
@@ -156,7 +160,6 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
     double inv_layers = 1.0 / layers;
     pin(inv_layers);
 
-    extern __shared__ __align__(128) unsigned char rrb_smem[];
     // G_tresh is a property of the catchment, not of the member: {G_tresh, 1/G_tresh, division span} per layer
     // live in shared memory and are only read by the steps that really divide by it
     uint32_t gtrec = 0;
@@ -401,10 +404,11 @@ template <int LC, class Gr4j, bool FAST, int FAMILY>
 static cudaError_t cema_launch_variant(const CemaArgs& a, const CemaOut& out, const Slab& slab, const Objective& obj,
                                        const LaunchCfg& cfg) {
     constexpr int R = CemaGeom<LC>::R, TT = CemaGeom<LC>::TT;
-    const int block = cfg.block > 0 ? cfg.block : pick_block(a.N * a.count, cfg.sm_count, a.N >= 128 ? 128 : 64);
+    int block = cfg.block > 0 ? cfg.block : pick_block(a.N * a.count, cfg.sm_count, a.N >= 128 ? 128 : 64);
+    if (Gr4j::kOrdSmemBytes > 0 && block > kOrdThreads) block = kOrdThreads;  // ordinate columns in shared memory
     const dim3 grid((unsigned)((a.N + block - 1) / block), (unsigned)a.count);
     const size_t smem = forcing_smem_bytes<R, TT>() + ((FAMILY & 1) ? 0 : 32 * LC) +
-                        ((FAST && Gr4j::kStateSlots > 0) ? fastmath_smem_bytes() : 0);
+                        ((FAST && Gr4j::kStateSlots > 0) ? fastmath_smem_bytes() : 0) + Gr4j::kOrdSmemBytes;
     const bool plain = out.q && !out.G && !obj.qobs;
 #define RRB_CEMA(P_, E_) cema_kernel<LC, Gr4j, FAST, P_, E_, FAMILY><<<grid, block, smem, cfg.stream>>>(a, out, slab, obj)
     if (FAMILY == 0) {

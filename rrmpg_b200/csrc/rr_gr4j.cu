@@ -69,8 +69,11 @@ __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double 
     const int64_t i = gi < N ? gi : N - 1;
     const bool WRITEQ = PLAIN || qsim != nullptr, STORAGE = !PLAIN && s_store != nullptr,
                OBJ = !PLAIN && obj.qobs != nullptr;  // CTA-uniform
+    extern __shared__ __align__(128) unsigned char rrb_smem[];
+    // dynamic shared memory = [forcing ring | FAST tables | unit hydrograph ordinates (long-hydrograph class only)]
+    constexpr size_t kOrdOff = forcing_smem_bytes<kGr4jR, kGr4jTT>() + (FAST ? fastmath_smem_bytes() : 0);
     Member m;
-    m.init(params + 4 * i, s_init, r_init);  // record = (x1, x2, x3, x4), rrmpg/models/gr4j.py:57-60
+    m.init(params + 4 * i, s_init, r_init, smem_u32(rrb_smem + kOrdOff));  // record = (x1, x2, x3, x4), gr4j.py:57-60
     double acc = 0.0;
     if (slab.t_begin > 0) {
         m.load(slab.state, N, i);
@@ -83,7 +86,6 @@ __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double 
     double* s_o = STORAGE ? s_store + off : nullptr;
     double* r_o = STORAGE ? r_store + off : nullptr;
 
-    extern __shared__ __align__(128) unsigned char rrb_smem[];
     uint32_t tb = 0;
     bool use_fast = false;
     Exp2Regs ek{};
@@ -160,9 +162,10 @@ template <class Member, bool FAST>
 static cudaError_t launch_variant(const double* F, int64_t T, double s_init, double r_init, const double* params, int64_t N,
                                   double* qsim, double* s_store, double* r_store, const Slab& slab,
                                   const Objective& obj, const LaunchCfg& cfg, const Batch& batch) {
-    const int block = cfg.block > 0 ? cfg.block : pick_block(N * batch.count, cfg.sm_count, N >= 128 ? 128 : 64);
+    int block = cfg.block > 0 ? cfg.block : pick_block(N * batch.count, cfg.sm_count, N >= 128 ? 128 : 64);
+    if (Member::kOrdSmemBytes > 0 && block > kOrdThreads) block = kOrdThreads;  // ordinate columns in shared memory
     const dim3 grid((unsigned)((N + block - 1) / block), (unsigned)batch.count);
-    const size_t smem = forcing_smem_bytes<kGr4jR, kGr4jTT>() + (FAST ? fastmath_smem_bytes() : 0);
+    const size_t smem = forcing_smem_bytes<kGr4jR, kGr4jTT>() + (FAST ? fastmath_smem_bytes() : 0) + Member::kOrdSmemBytes;
     const uint32_t* fflag = forcing_flag(F, T, kGr4jTT, kGr4jR);
     if (qsim && !s_store && !obj.qobs)
         gr4j_kernel<Member, FAST, true><<<grid, block, smem, cfg.stream>>>(F, s_init, r_init, params, N, qsim, s_store,

@@ -25,18 +25,47 @@ static __device__ __noinline__ double gr4j_s_curve2(int t, double x4) {  // gr4j
     else return 1.0;
 }
 
-template <int C1, int C2, int MATH>
+// OSMEM: the unit hydrograph ordinates (per member, constant over the series) live in shared memory instead of
+// registers -- slot j of thread tid at ord + j * kOrdStride, a conflict-free column layout for CTAs of at most
+// kOrdThreads threads.  Used by the long-hydrograph class (x4 <= 10: 31 ordinates + 31 state slots per member would
+// otherwise take 124 registers and push the coupled kernels into local-memory spills).
+constexpr int kOrdThreads = 64;
+
+template <int C1, int C2, int MATH, bool OSMEM = false>
 struct Gr4jMember {
     double x1, x2, x3;
     double inv_x1, inv_x3, k_tanh, k49;  // FAST: 1/x1, 1/x3, 2 log2(e) / x1, (4/9) / x1
     int n1, n2;
-    double o1[C1], o2[C2];  // unit hydrograph ordinates
+    double o1[OSMEM ? 1 : C1], o2[OSMEM ? 1 : C2];  // unit hydrograph ordinates (registers)
+    uint32_t ord;                                   // OSMEM: shared address of this thread's ordinate column
     double u1[C1], u2[C2];  // routed water still in the unit hydrographs
     double S, R;            // production / routing store
 
     static constexpr int kStateSlots = 2 + C1 + C2;
+    static constexpr uint32_t kOrdStride = kOrdThreads * 8;
+    static constexpr size_t kOrdSmemBytes = OSMEM ? (size_t)(C1 + C2) * kOrdStride : 0;
 
-    __device__ __forceinline__ void init(const double* p /* x1,x2,x3,x4 */, double s_init, double r_init) {
+    __device__ __forceinline__ double O1(int j) const {
+        if constexpr (OSMEM) return lds_f64(ord + (uint32_t)j * kOrdStride);
+        else return o1[j];
+    }
+    __device__ __forceinline__ double O2(int j) const {
+        if constexpr (OSMEM) return lds_f64(ord + (uint32_t)(C1 + j) * kOrdStride);
+        else return o2[j];
+    }
+    __device__ __forceinline__ void set_ord(int slot, double v) {  // slot < C1: UH1, else UH2
+        if constexpr (OSMEM) {
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(ord + (uint32_t)slot * kOrdStride), "d"(v) : "memory");
+        } else {
+            if (slot < C1) o1[slot] = v;
+            else o2[slot - C1] = v;
+        }
+    }
+
+    // ord_addr: shared address of the CTA's ordinate block (OSMEM only; every thread of the CTA passes the same)
+    __device__ __forceinline__ void init(const double* p /* x1,x2,x3,x4 */, double s_init, double r_init,
+                                         uint32_t ord_addr = 0) {
+        ord = ord_addr + threadIdx.x * 8u;
         x1 = p[0]; x2 = p[1]; x3 = p[2];
         const double x4 = p[3];
         inv_x1 = 1.0 / x1; inv_x3 = 1.0 / x3;
@@ -52,12 +81,12 @@ struct Gr4jMember {
         n2 = n2 < 1 ? 1 : (n2 > C2 ? C2 : n2);
 #pragma unroll
         for (int j = 1; j <= C1; ++j) {
-            o1[j - 1] = gr4j_s_curve1(j, x4) - gr4j_s_curve1(j - 1, x4);  // :75-76
+            set_ord(j - 1, gr4j_s_curve1(j, x4) - gr4j_s_curve1(j - 1, x4));  // :75-76
             u1[j - 1] = 0.0;
         }
 #pragma unroll
         for (int j = 1; j <= C2; ++j) {
-            o2[j - 1] = gr4j_s_curve2(j, x4) - gr4j_s_curve2(j - 1, x4);  // :78-79
+            set_ord(C1 + j - 1, gr4j_s_curve2(j, x4) - gr4j_s_curve2(j - 1, x4));  // :78-79
             u2[j - 1] = 0.0;
         }
     }
@@ -94,9 +123,9 @@ struct Gr4jMember {
     // FAST folds the 0.9 / 0.1 split of the routed water (:126-127) into the unit hydrograph ordinates
     __device__ __forceinline__ void enter_fast() {
 #pragma unroll
-        for (int j = 0; j < C1; ++j) o1[j] *= 0.9;
+        for (int j = 0; j < C1; ++j) set_ord(j, O1(j) * 0.9);
 #pragma unroll
-        for (int j = 0; j < C2; ++j) o2[j] *= 0.1;
+        for (int j = 0; j < C2; ++j) set_ord(C1 + j, O2(j) * 0.1);
     }
 
     // one timestep: P = precipitation (or Cemaneige liquid outflow), E = potential evapotranspiration
@@ -124,16 +153,16 @@ struct Gr4jMember {
         // unit hydrographs, :130-136
 #pragma unroll
         for (int j = 0; j < C1 - 1; ++j) {
-            const double add = o1[j] * p1;
+            const double add = O1(j) * p1;
             u1[j] = (j == n1 - 1) ? add : u1[j + 1] + add;
         }
-        u1[C1 - 1] = o1[C1 - 1] * p1;
+        u1[C1 - 1] = O1(C1 - 1) * p1;
 #pragma unroll
         for (int j = 0; j < C2 - 1; ++j) {
-            const double add = o2[j] * p2;
+            const double add = O2(j) * p2;
             u2[j] = (j == n2 - 1) ? add : u2[j + 1] + add;
         }
-        u2[C2 - 1] = o2[C2 - 1] * p2;
+        u2[C2 - 1] = O2(C2 - 1) * p2;
         const double gw = x2 * pow(R / x3, 3.5);  // :139
         R = nb_max0(R + u1[0] + gw);              // :142
         const double v = R / x3;
@@ -175,11 +204,11 @@ struct Gr4jMember {
         const double p_n = wet ? arg - frac : 0.0;
         const double p_r = perc + p_n;
 #pragma unroll
-        for (int j = 0; j < C1 - 1; ++j) u1[j] = fma(o1[j], p_r, u1[j + 1]);
-        u1[C1 - 1] = o1[C1 - 1] * p_r;
+        for (int j = 0; j < C1 - 1; ++j) u1[j] = fma(O1(j), p_r, u1[j + 1]);
+        u1[C1 - 1] = O1(C1 - 1) * p_r;
 #pragma unroll
-        for (int j = 0; j < C2 - 1; ++j) u2[j] = fma(o2[j], p_r, u2[j + 1]);
-        u2[C2 - 1] = o2[C2 - 1] * p_r;
+        for (int j = 0; j < C2 - 1; ++j) u2[j] = fma(O2(j), p_r, u2[j + 1]);
+        u2[C2 - 1] = O2(C2 - 1) * p_r;
         const double gw = x2 * pow35_sane(R * inv_x3, k);
         R = max0_sane((R + u1[0]) + gw);
         const double v = R * inv_x3;
@@ -206,8 +235,8 @@ using Gr4jUh3F = Gr4jMember<3, 7, RRB_MATH_FAST_>;
 using Gr4jUh3P = Gr4jMember<3, 7, RRB_MATH_PRECISE_>;
 using Gr4jUh4F = Gr4jMember<4, 9, RRB_MATH_FAST_>;
 using Gr4jUh4P = Gr4jMember<4, 9, RRB_MATH_PRECISE_>;
-using Gr4jUh10F = Gr4jMember<10, 21, RRB_MATH_FAST_>;
-using Gr4jUh10P = Gr4jMember<10, 21, RRB_MATH_PRECISE_>;
+using Gr4jUh10F = Gr4jMember<10, 21, RRB_MATH_FAST_, true>;
+using Gr4jUh10P = Gr4jMember<10, 21, RRB_MATH_PRECISE_, true>;
 
 // generic fallback for very long unit hydrographs (x4 beyond the register variants): buffers
 // in per-thread local memory with run-time lengths, PRECISE arithmetic only.  x4 <= 64.
@@ -221,8 +250,9 @@ struct Gr4jMemberDyn {
     double S, R;
 
     static constexpr int kStateSlots = 2 + kGr4jGenericC1 + kGr4jGenericC2;
+    static constexpr size_t kOrdSmemBytes = 0;
 
-    __device__ void init(const double* p, double s_init, double r_init) {
+    __device__ void init(const double* p, double s_init, double r_init, uint32_t = 0) {
         x1 = p[0]; x2 = p[1]; x3 = p[2];
         const double x4 = p[3];
         S = s_init * x1;

@@ -289,6 +289,6 @@ __device__ __forceinline__ const FastTables* fastmath_tables_to_smem(unsigned ch
 }
 #endif
 
-constexpr size_t fastmath_smem_bytes() { return sizeof(FastTables); }
+__host__ __device__ constexpr size_t fastmath_smem_bytes() { return sizeof(FastTables); }
 
 }  // namespace rrb

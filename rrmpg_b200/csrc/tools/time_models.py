@@ -46,6 +46,9 @@ if N <= 131072:  # all five outputs: 40 B per member-step, 38 GB at 65 536 membe
 P = t(engine.pack_params(synthetic.random_params(GR4J(), N)))
 etp = t(f["etp"])
 report("GR4J", timeit(lambda: engine.gr4j(prec, etp, 0.6, 0.7, P, out=out, math=math, x4_max=2.9)))
+Pl = synthetic.random_params(GR4J(), N); Pl["x4"] = np.random.default_rng(3).uniform(0.5, 10.0, N)
+P = t(engine.pack_params(Pl))
+report("GR4J x4<=10 (long UH class)", timeit(lambda: engine.gr4j(prec, etp, 0.6, 0.7, P, out=out, math=math, x4_max=10.0)))
 lp, lt, fr, L = _snow_inputs.to_layers(f["prec"], f["temp"], f["min_temp"], f["max_temp"], synthetic.MET_STATION_HEIGHT,
                                        np.array(synthetic.ALTITUDES))
 lp, lt, fr = t(lp), t(lt), t(fr)
