@@ -226,7 +226,14 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
 
     // one timestep; FIRST = the very first step of the series, where the stores take their initial values
     // instead of being updated (cemaneige_model.py:85-92, cemaneigehyst_model.py:107-115)
-    auto step = [&](auto first_c, auto fast_c, auto snow_c, int64_t t, const double* f) {
+    // The step has two parts: the snow routine (all layers) -> liquid water, and the routing of that water (GR4J,
+    // outputs).  The snow routine of step t+1 only needs the snow states of step t, so the coupled kernels run two
+    // steps per loop trip -- snow(t), snow(t+1), route(t), route(t+1) in one basic block -- and the scheduler overlaps
+    // the snow routine of the next step with the long GR4J chain of the current one.
+    struct SnowOut {
+        double liquid, ice_sum, snowmelt;
+    };
+    auto snow_part = [&](auto first_c, auto snow_c, const double* f) -> SnowOut {
         constexpr bool FIRST = decltype(first_c)::value != 0;
         constexpr bool CONTRACT = decltype(snow_c)::value != 0;
         double lw_sum = 0.0, ice_sum = 0.0;
@@ -310,18 +317,23 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
         // np.mean over the layers (:124-125); x / 1 == x
         const double snowmelt = (L == 1) ? lw_sum : div_by_invariant(lw_sum, layers, inv_layers, kDivSpanOk);
         const double liquid = ICE ? snowmelt + ice_sum : snowmelt;        // cemaneigegr4jice_model.py:87
-        double qv = liquid;
+        if (STORAGE) {
+            G_o += strideL;
+            E_o += strideL;
+            if (HYST) S_o += strideL;
+        }
+        return SnowOut{liquid, ice_sum, snowmelt};
+    };
+    auto route_part = [&](auto fast_c, const SnowOut& w, double etp_t, int64_t t) {
+        double qv = w.liquid;
         if constexpr (COUPLED) {                                          // cemaneigegr4j_model.py:62
-            qv = gr4j_step(fast_c, gr, liquid, f[3 * LC], tb, ek);
+            qv = gr4j_step(fast_c, gr, w.liquid, etp_t, tb, ek);
         }
         if (WRITEQ) {
             st_stream(q_o, qv);
             q_o += stride;
         }
         if (STORAGE) {
-            G_o += strideL;
-            E_o += strideL;
-            if (HYST) S_o += strideL;
             if constexpr (COUPLED) {
                 st_stream(s_o, gr.S);
                 st_stream(r_o, gr.R);
@@ -329,11 +341,11 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
                 r_o += stride;
             }
             if (ICE) {
-                st_stream(im_o, ice_sum);
+                st_stream(im_o, w.ice_sum);
                 im_o += stride;
             }
             if (FAMILY == 3) {
-                st_stream(sm_o, snowmelt);
+                st_stream(sm_o, w.snowmelt);
                 sm_o += stride;
             }
         }
@@ -342,6 +354,11 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
             acc += d * d;
         }
     };
+    auto step = [&](auto first_c, auto fast_c, auto snow_c, int64_t t, const double* f) {
+        const SnowOut w = snow_part(first_c, snow_c, f);
+        route_part(fast_c, w, f[3 * LC], t);
+    };
+    constexpr int GROUP = (COUPLED && LC <= 5) ? 2 : 1;
 
     auto run = [&](auto fast_c, auto snow_c) {
         int64_t t_first = slab.t_begin;
@@ -352,8 +369,15 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
             step(ic<1>{}, fast_c, snow_c, 0, f0);
             t_first = 1;
         }
-        stream_forcing_grouped<R, TT, 1, CemaF<LC>>(F, t_first, slab.t_end, [&](auto, int64_t t, const CemaF<LC>* fp) {
-            step(ic<0>{}, fast_c, snow_c, t, fp[0].v);
+        stream_forcing_grouped<R, TT, GROUP, CemaF<LC>>(F, t_first, slab.t_end, [&](auto gc, int64_t t, const CemaF<LC>* fp) {
+            if constexpr (decltype(gc)::value == 2) {
+                const SnowOut w0 = snow_part(ic<0>{}, snow_c, fp[0].v);
+                const SnowOut w1 = snow_part(ic<0>{}, snow_c, fp[1].v);
+                route_part(fast_c, w0, fp[0].v[3 * LC], t);
+                route_part(fast_c, w1, fp[1].v[3 * LC], t + 1);
+            } else {
+                step(ic<0>{}, fast_c, snow_c, t, fp[0].v);
+            }
         });
     };
     if constexpr (COUPLED && FAST) {
