@@ -63,7 +63,12 @@ struct CemaF {  // forcing of one timestep: { snow[LC] | rain[LC] | mean_temp[LC
 };
 
 // numba's max(a, b) / min(a, b) on floats: (b > a) ? b : a and (b < a) ? b : a (probed against numba)
-__device__ __forceinline__ double nb_max(double a, double b) { return (b > a) ? b : a; }
+// (setp + selp like nb_min in rr_common.cuh: the C++ ternary is pattern-matched into a DSETP.MAX + NaN fix-up sequence)
+__device__ __forceinline__ double nb_max(double a, double b) {
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %2, %1;\n\tselp.f64 %0, %2, %1, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
 
 // PLAIN = discharge only (no storages, no fused objective): the output flags are compile-time constants
 // EXACT = the run has exactly LC layers (L == LC): the per-layer bound checks fold away
