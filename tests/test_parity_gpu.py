@@ -743,3 +743,19 @@ def test_randomized_parity_sweep_all_models():
     print("\nworst relative deviation from the oracle (|ref| > 1e-6), FAST math: "
           + ", ".join(f"{k} {v:.1e}" for k, v in sorted(worst.items())))
     assert max(worst.values()) < 1e-10
+
+
+@pytest.mark.parametrize("N", [2, 64, 1000, 1001])
+def test_abc_pair_kernel_and_scalar_kernel_are_bit_identical(N):
+    """Even ensembles take the two-members-per-thread kernel with 16-byte stores, odd ones (and any call with
+    storages / an objective) the scalar kernel; both bit-identical to the oracle, also across time slabs."""
+    f = synthetic.forcing(700, seed=21)
+    P = synthetic.random_params(ABCModel(), N, seed=22)
+    ref = oracle.abc(f["prec"], 1.5, P, return_storage=True)
+    one = engine.abc(f["prec"], 1.5, P)["qsim"]
+    assert_bits_equal(one, ref[0], f"abc N={N}")
+    for slab in (1, 7, 128):
+        assert_bits_equal(engine.abc(f["prec"], 1.5, P, slab_steps=slab)["qsim"], ref[0], f"abc N={N} slab={slab}")
+    both = engine.abc(f["prec"], 1.5, P, return_storage=True)
+    assert_bits_equal(both["qsim"], ref[0], "abc qsim with storage")
+    assert_bits_equal(both["storage"], ref[1], "abc storage")
