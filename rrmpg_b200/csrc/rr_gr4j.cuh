@@ -110,15 +110,17 @@ struct Gr4jMember {
 
     // ---- FAST path contract -----------------------------------------------------------------------
     // step_fast() carries no special-value handling: it is only entered when every member of the CTA is
-    // "sane" (finite parameters of moderate magnitude, finite initial states) and the packed forcing is
+    // "sane" (finite parameters of moderate magnitude, initial fractions within [0, 1]) and the packed forcing is
     // finite and moderately ranged (flag written by the pack kernel).  Then every store stays finite
     // (S <= 2.25 x1 + P and R <= x3 + UH water after each step), no operand can reach the ranges where the
     // branch-free sequences of rr_math.cuh differ from libm, and NaN never appears.  Otherwise the CTA runs
     // step_precise(): the reference's operations, special values included.
     bool sane;
     __device__ __forceinline__ void judge(const double* p, double s_init, double r_init) {
+        // initial fractions within [0, 1] like the wrapper enforces (gr4j.py:136-144): a negative routing store would
+        // make (R/x3)^3.5 a NaN that numba's max(0, NaN) = 0 silently absorbs -- reference-order arithmetic only
         sane = p[0] >= 1e-3 && p[0] <= 1e6 && p[2] >= 1e-3 && p[2] <= 1e6 && fabs(p[1]) <= 1e4 && p[3] > 0.0 &&
-               p[3] <= 64.0 && fabs(s_init) <= 1e3 && fabs(r_init) <= 1e3;
+               p[3] <= 64.0 && s_init >= 0.0 && s_init <= 1.0 && r_init >= 0.0 && r_init <= 1.0;
     }
     // FAST folds the 0.9 / 0.1 split of the routed water (:126-127) into the unit hydrograph ordinates
     __device__ __forceinline__ void enter_fast() {

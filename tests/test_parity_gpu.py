@@ -306,6 +306,14 @@ def test_gr4j_fast_path_contract_falls_back_to_reference_arithmetic():
     got = engine.gr4j(f["prec"] * 0, f["etp"], 0.0, 0.0, P, return_storage=True, math="fast")
     for nm, r in zip(["qsim", "s_store", "r_store"], ref):
         assert_close(got[nm], r, "gr4j dry catchment " + nm)
+    # initial fractions outside [0, 1] (the wrapper rejects them, the C ABI does not): a negative routing store makes
+    # (R/x3)^3.5 a NaN that numba's max(0, NaN) = 0 absorbs -- such calls take the reference-order step
+    P = synthetic.random_params(GR4J(), 64, seed=9)
+    for si, ri in ((0.5, -0.3), (-0.4, 0.5), (1.7, 2.5)):
+        ref = oracle.gr4j(f["prec"], f["etp"], si, ri, P, return_storage=True)
+        got = engine.gr4j(f["prec"], f["etp"], si, ri, P, return_storage=True, math="fast")
+        for nm, r in zip(["qsim", "s_store", "r_store"], ref):
+            assert_close(got[nm], r, f"gr4j inits ({si}, {ri}) " + nm)
     # an extreme storm relative to a tiny production store: tanh saturates (argument clamp of the FAST path)
     P = synthetic.random_params(GR4J(), 64, seed=8)
     P["x1"][:] = np.linspace(0.01, 5.0, 64)
