@@ -58,3 +58,36 @@ def test_exp2m1_is_relatively_accurate_down_to_zero():
     # saturation used by the tanh formula: clamp at z = 64
     assert _exp2m1(np.array([64.0, 500.0, np.inf]))[1] == _exp2m1(np.array([64.0]))[0]
     assert np.isnan(_exp2m1(np.array([np.nan]))[0])
+
+
+def test_third_order_corrections_of_the_seed_units():
+    """rr_math.cuh: rcp_sane / rsqrt4_sane / pow35_sane refine a MUFU.RCP64H / MUFU.RSQ64H seed (which only sees and
+    only produces the high 32 bits of a double: ~2^-20 relative) with ONE third-order correction.  The same arithmetic
+    in numpy, with seeds truncated to their high word, stays within a few ulp over the operand ranges of the kernels."""
+    rng = np.random.default_rng(5)
+    hi_only = lambda a: (np.ascontiguousarray(a).view(np.uint64) & np.uint64(0xFFFFFFFF00000000)).view(np.float64)
+    seed_rsq = lambda x: hi_only(1.0 / np.sqrt(hi_only(x)))
+    seed_rcp = lambda x: hi_only(1.0 / hi_only(x))
+    ulp = 2.0 ** -52
+    # v^(-1/4) for v = 1 + u^4 >= 1: y (1 + e/4 + 5 e^2/32), e = 1 - v y^4
+    v = 1.0 + rng.random(200000) ** 4 * 10.0 ** rng.uniform(-8, 40, 200000)
+    a = seed_rsq(v)
+    y = a * seed_rsq(a)
+    assert np.max(np.abs(y * v ** 0.25 - 1)) < 2.0 ** -18          # the double seed
+    y2 = y * y
+    e = 1.0 - v * (y2 * y2)
+    y = y + y * (e * (e * 0.15625 + 0.25))
+    assert np.max(np.abs(y * v ** 0.25 - 1)) < 4 * ulp
+    # w^3.5 = w^4 w^(-1/2): y (1 + e/2 + 3 e^2/8), e = 1 - w y^2
+    w = 10.0 ** rng.uniform(-30, 9, 200000)
+    y0 = seed_rsq(w)
+    e = 1.0 - (w * y0) * y0
+    y = y0 + (y0 * e) * (e * 0.375 + 0.5)
+    w2 = w * w
+    assert np.max(np.abs((w2 * w2) * y / w ** 3.5 - 1)) < 6 * ulp
+    # 1/den for den >= 2: y (1 + e + e^2), e = 1 - den y
+    den = 2.0 + 10.0 ** rng.uniform(-6, 20, 200000)
+    y0 = seed_rcp(den)
+    e = 1.0 - den * y0
+    y = y0 + y0 * (e * e + e)
+    assert np.max(np.abs(y * den - 1)) < 4 * ulp
