@@ -91,3 +91,62 @@ def test_third_order_corrections_of_the_seed_units():
     e = 1.0 - den * y0
     y = y0 + y0 * (e * e + e)
     assert np.max(np.abs(y * den - 1)) < 4 * ulp
+
+
+def test_gr4j_fast_step_algebra_matches_the_reference_recurrence():
+    """Host twin of Gr4jMember::step_fast (rr_gr4j.cuh) in numpy -- the branch-free formulation (wet / dry through the
+    sign of P - E, tanh as m / (m + 2) with m = expm1(2a), both production-store branches as num m / (2 + c m),
+    S (1 - y) as one product, 0.9 / 0.1 folded into the ordinates) -- against the oracle's reference-order recurrence.
+    Exact libm functions stand in for the seed-unit sequences (covered by the test above)."""
+    import oracle
+    from rrmpg_b200 import synthetic
+    from rrmpg_b200.models import GR4J
+    T, N = 600, 300
+    f = synthetic.forcing(T, seed=31)
+    P = synthetic.random_params(GR4J(), N, seed=32)
+    x1, x2, x3, x4 = (P[k].astype(np.float64) for k in ("x1", "x2", "x3", "x4"))
+    C1, C2 = 3, 7
+    sc1 = lambda t: np.where(t <= 0, 0.0, np.where(t < x4, (np.maximum(t, 0) / x4) ** 2.5, 1.0))
+    def sc2(t):
+        r = np.where(t <= 0, 0.0, 0.5 * (np.maximum(t, 0) / x4) ** 2.5)
+        r = np.where((t > x4) & (t < 2 * x4), 1 - 0.5 * np.abs(2 - t / x4) ** 2.5, r)
+        return np.where(t >= 2 * x4, 1.0, r)
+    o1 = [0.9 * (sc1(j) - sc1(j - 1)) for j in range(1, C1 + 1)]
+    o2 = [0.1 * (sc2(j) - sc2(j - 1)) for j in range(1, C2 + 1)]
+    u1 = [np.zeros(N) for _ in range(C1)]
+    u2 = [np.zeros(N) for _ in range(C2)]
+    S, R = 0.6 * x1, 0.7 * x3
+    inv_x1, inv_x3, k49 = 1.0 / x1, 1.0 / x3, (4.0 / 9.0) / x1
+    q = np.empty((T, N))
+    for t in range(T):
+        d = f["prec"][t] - f["etp"][t]
+        wet = d >= 0
+        arg = abs(d)
+        sr = S * inv_x1
+        m = np.expm1(2.0 * arg * inv_x1)
+        sgn = 1.0 if wet else -1.0
+        c = sgn * sr + (1.0 if wet else 2.0)
+        base = x1 if wet else S + S
+        num = base - S * sr
+        frac = (num * m) / (c * m + 2.0)
+        S = S + sgn * frac
+        u = S * k49
+        perc = S - S * (1.0 + (u * u) ** 2) ** -0.25
+        S = S - perc
+        p_r = perc + ((arg - frac) if wet else 0.0)
+        for j in range(C1 - 1):
+            u1[j] = o1[j] * p_r + u1[j + 1]
+        u1[C1 - 1] = o1[C1 - 1] * p_r
+        for j in range(C2 - 1):
+            u2[j] = o2[j] * p_r + u2[j + 1]
+        u2[C2 - 1] = o2[C2 - 1] * p_r
+        w = R * inv_x3
+        gw = x2 * (w ** 4 / np.sqrt(np.where(w > 0, w, 1.0)))
+        R = np.maximum(0.0, (R + u1[0]) + gw)
+        v = R * inv_x3
+        q_r = R - R * (1.0 + (v * v) ** 2) ** -0.25
+        R = R - q_r
+        q[t] = q_r + np.maximum(0.0, u2[0] + gw)
+    ref = oracle.gr4j(f["prec"], f["etp"], 0.6, 0.7, P)
+    assert np.allclose(q, ref, rtol=1e-10, atol=1e-12)
+    assert np.max(np.abs(q - ref) / (np.abs(ref) + 1e-6)) < 1e-11
