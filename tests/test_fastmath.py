@@ -150,3 +150,44 @@ def test_gr4j_fast_step_algebra_matches_the_reference_recurrence():
     ref = oracle.gr4j(f["prec"], f["etp"], 0.6, 0.7, P)
     assert np.allclose(q, ref, rtol=1e-10, atol=1e-12)
     assert np.max(np.abs(q - ref) / (np.abs(ref) + 1e-6)) < 1e-11
+
+
+def test_hbv_fast_snow_routine_is_bitwise_the_reference_one_for_finite_rain():
+    """rr_hbvedu.cu (FAST): melt = min(snow, m) serves max(0, snow - m) = snow - melt and the liquid water
+    prec + melt; the cold branch is the same two additions with -prec in place of melt.  Elementwise, on random and
+    adversarial operands, both formulations give the same bits (hbvedu_model.py:87-96)."""
+    rng = np.random.default_rng(9)
+    n = 400000
+    snow = np.where(rng.random(n) < 0.3, 0.0, rng.gamma(1.0, 20.0, n))
+    prec = np.where(rng.random(n) < 0.5, 0.0, rng.gamma(0.8, 6.0, n))
+    temp = rng.normal(2.0, 8.0, n)
+    T_t = rng.uniform(-3, 3, n)
+    DD = rng.uniform(0.5, 5, n)
+    # adversarial: exact ties and zeros
+    snow[:1000] = DD[:1000] * (temp[:1000] - T_t[:1000])
+    temp[1000:2000] = T_t[1000:2000]
+    prec[2000:3000] = 0.0
+    snow[3000:4000] = -rng.random(1000)          # a negative pack (negative snow_init)
+    m = DD * (temp - T_t)
+    cold = temp < T_t
+    # reference (numba semantics: max(0, x) = x if x > 0 else 0; min(a, b) = b if b < a else a)
+    d = snow - m
+    ref_snow = np.where(cold, snow + prec, np.where(d > 0, d, 0.0))
+    ref_liq = np.where(cold, 0.0, prec + np.where(m < snow, m, snow))
+    # FAST formulation
+    melt = np.where(m < snow, m, snow)
+    sel = np.where(np.signbit(temp - T_t), -prec, melt)       # cold read off the sign of temp - T_t
+    got_snow = snow - sel
+    got_liq = prec + sel
+    same = lambda a, b: np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    assert same(got_snow, ref_snow)
+    assert same(got_liq, ref_liq)
+
+
+def test_cemaneige_contract_absorbs_the_quotient_of_a_vanishing_pack():
+    """rr_cemaneige.cuh, contract step: for a pack below 2^-960 the unchecked Markstein quotient G / G_tresh may have
+    wrong low bits, but it stays below 2^-900 (G_tresh >= 2^-60) and 0.9 ratio + 0.1 rounds to 0.1 for every ratio
+    below 2^-58 -- exactly what the reference computes from the exact tiny quotient (cemaneige_model.py:109-115)."""
+    r = np.concatenate([2.0 ** -np.arange(58, 1075, dtype=np.float64), [0.0, 5e-324]])
+    assert np.all(0.9 * r + 0.1 == 0.1)
+    assert 0.9 * 2.0 ** -52 + 0.1 != 0.1          # ... and not for quotients that matter
