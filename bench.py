@@ -161,13 +161,14 @@ def run_reference(args):
     return 0
 
 
-def config_dict(n_gpus):
-    return {"workload": f"HBVEdu {MEMBERS_PER_GPU} members per GPU x {T_STEPS} daily steps (BASELINE.json configs[1]), "
+def config_dict(n_gpus, members=MEMBERS_PER_GPU):
+    which = "BASELINE.json configs[1]" if members == MEMBERS_PER_GPU else "configs[1] at a non-default ensemble size"
+    return {"workload": f"HBVEdu {members} members per GPU x {T_STEPS} daily steps ({which}), "
                         "qsim-only output [T, N] fp64",
-            "members_per_gpu": MEMBERS_PER_GPU, "timesteps": T_STEPS, "global_members": MEMBERS_PER_GPU * n_gpus,
+            "members_per_gpu": members, "timesteps": T_STEPS, "global_members": members * n_gpus,
             "parallelism": f"member-block x{n_gpus}" if n_gpus > 1 else "single GPU",
             "math": "fast",
-            "l2": "no explicit flush: every step streams its 7.66 GB discharge array through the 126 MB L2"}
+            "l2": f"no explicit flush: every step streams its {members * T_STEPS * 8 / 1e9:.2f} GB discharge array through the 126 MB L2"}
 
 
 def main():
@@ -311,7 +312,7 @@ def main():
         cpu, _ = cpu_baseline_run(f, P)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config_dict(world), "roofline": roofline,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(world, members), "roofline": roofline,
             "issue_roofline": issue, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP[args.math] * args.steps, "clocks": clocks,
             "parity_spot_check": parity}
     line["config"]["math"] = args.math
