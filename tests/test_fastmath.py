@@ -191,3 +191,45 @@ def test_cemaneige_contract_absorbs_the_quotient_of_a_vanishing_pack():
     r = np.concatenate([2.0 ** -np.arange(58, 1075, dtype=np.float64), [0.0, 5e-324]])
     assert np.all(0.9 * r + 0.1 == 0.1)
     assert 0.9 * 2.0 ** -52 + 0.1 != 0.1          # ... and not for quotients that matter
+
+
+def test_hbv_fast_step_algebra_matches_the_reference_recurrence():
+    """Host twin of hbv_fast_kernel (rr_hbvedu.cu) in numpy: FAST forcing packing (dT * PEm), hoisted reciprocals and
+    linear-store coefficients, the select-based snow routine, pow skipped where liquid water is zero, sign-bit
+    max(0, s1 - L) -- against the oracle's reference-order recurrence (hbvedu_model.py:84-127)."""
+    import oracle
+    from rrmpg_b200 import synthetic
+    from rrmpg_b200.models import HBVEdu
+    T, N = 800, 400
+    f = synthetic.forcing(T, seed=41)
+    P = synthetic.random_params(HBVEdu(), N, seed=42)
+    g = lambda k: P[k].astype(np.float64)
+    T_t, DD, FC, Beta, C, PWP, K_0, K_1, K_2, K_p, L = (g(k) for k in
+                                                       ("T_t", "DD", "FC", "Beta", "C", "PWP", "K_0", "K_1", "K_2", "K_p", "L"))
+    m0 = f["month"] - 1
+    dTPEm = (f["temp"] - f["T_m"][m0]) * f["PE_m"][m0]      # FAST packing of the pack kernel
+    PEm = f["PE_m"][m0]
+    inv_FC, inv_PWP, c1, c2 = 1.0 / FC, 1.0 / PWP, 1.0 - K_1 - K_p, 1.0 - K_2
+    snow, soil, s1, s2 = np.zeros(N), np.full(N, 100.0), np.full(N, 3.0), np.full(N, 10.0)
+    q = np.zeros((T, N))
+    for t in range(1, T):
+        dtt = f["temp"][t] - T_t
+        m = DD * dtt
+        melt = np.where(m < snow, m, snow)
+        sel = np.where(np.signbit(dtt), -f["prec"][t], melt)
+        snow = snow - sel
+        liquid = f["prec"][t] + sel
+        pe = C * dTPEm[t] + PEm[t]
+        ea = np.where(soil > PWP, pe, pe * (soil * inv_PWP))
+        x = s1 - L
+        oK = np.where(np.signbit(x), 0.0, x) * K_0
+        s2_new = s1 * K_p + s2 * c2
+        s1_new = s1 * c1 - oK
+        soil_new = (soil + liquid) - ea
+        wet = liquid != 0
+        prec_eff = np.where(wet, liquid * np.power(soil * inv_FC, Beta, where=wet, out=np.ones(N)), 0.0)
+        soil, s1, s2 = soil_new - prec_eff, s1_new + prec_eff, s2_new
+        q[t] = s2 * K_2 + (s1 * K_1 + oK)
+    ref = oracle.hbvedu(f["temp"], f["prec"], m0, f["PE_m"], f["T_m"], (0, 100, 3, 10), P)
+    assert np.allclose(q, ref, rtol=1e-10, atol=1e-12)
+    assert np.max(np.abs(q - ref) / (np.abs(ref) + 1e-6)) < 1e-12
