@@ -47,6 +47,8 @@ def lib():
         _lib.oracle_gr4j_batch.restype = C.c_int
         _lib.oracle_cemaneigegr4j_batch.restype = C.c_int
         _lib.oracle_snowice_gr4j_batch.restype = C.c_int
+        _lib.oracle_check_invariant_division.restype = C.c_int64
+        _lib.oracle_check_invariant_division.argtypes = [C.c_int64, C.c_uint64, C.c_int]
     return _lib
 
 
@@ -219,3 +221,8 @@ def mse_columns(qobs, qsim):
     out = np.zeros(N)
     lib().oracle_mse_columns(_d(qobs), _d(qsim), C.c_int64(T), C.c_int64(N), _d(out))
     return out
+
+
+def check_invariant_division(n, seed=1, mode=0):
+    """Mismatches of the kernels' division-by-an-invariant sequence against IEEE division over n operand pairs."""
+    return int(lib().oracle_check_invariant_division(int(n), int(seed), int(mode)))

@@ -705,3 +705,55 @@ void oracle_mse_columns(const double *qobs, const double *qsim, int64_t T, int64
         mse[i] = acc / (double)T;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Test helper, not part of the reference: the division by a loop-invariant divisor that the CUDA
+ * kernels use in place of IEEE division where bit-exactness is required (rr_common.cuh:
+ * div_by_invariant; rr_cemaneige.cuh: the contract step evaluates G / G_tresh with it).  With
+ * y = RN(1/b): q = RN(a y); r = fma(-b, q, a); q = fma(r, y, q); r = fma(-b, q, a); q = fma(r, y, q).
+ * Returns how many of n pseudo-random operand pairs give a result different from a / b.
+ *   mode 0: b log-uniform in [2^-60, 2^60], a log-uniform in [2^-960, 2^960)   (the range test of the kernel)
+ *   mode 1: the snow-cover ratio: b log-uniform in [2^-20, 2^20], a = u b with u in (0, 1]
+ *   mode 2: adversarial: a = k b (+- a few ulp) for small integers k and their reciprocals
+ * fma() is exact (hardware FMA or glibc's software fma), the TU is built with -ffp-contract=off.
+ * ------------------------------------------------------------------------------------------ */
+static uint64_t oracle_rng(uint64_t *s)
+{
+    uint64_t x = *s;
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    return *s = x;
+}
+static double oracle_u01(uint64_t *s) { return (double)(oracle_rng(s) >> 11) * 0x1.0p-53; }
+static double oracle_invariant_div(double a, double b, double y)
+{
+    double q = a * y;
+    double r = fma(-b, q, a);
+    q = fma(r, y, q);
+    r = fma(-b, q, a);
+    q = fma(r, y, q);
+    return q;
+}
+int64_t oracle_check_invariant_division(int64_t n, uint64_t seed, int mode)
+{
+    uint64_t s = seed ? seed : 88172645463325252ULL;
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        double a, b;
+        if (mode == 0) {
+            b = ldexp(1.0 + oracle_u01(&s), (int)(oracle_rng(&s) % 120) - 60);
+            a = ldexp(1.0 + oracle_u01(&s), (int)(oracle_rng(&s) % 1920) - 960);
+        } else if (mode == 1) {
+            b = ldexp(1.0 + oracle_u01(&s), (int)(oracle_rng(&s) % 40) - 20);
+            a = b * (1.0 - oracle_u01(&s));
+        } else {
+            b = ldexp(1.0 + oracle_u01(&s), (int)(oracle_rng(&s) % 120) - 60);
+            const double k = (double)(1 + oracle_rng(&s) % 64);
+            a = (oracle_rng(&s) & 1) ? b * k : b / k;
+            const int nudge = (int)(oracle_rng(&s) % 5) - 2;
+            for (int j = 0; j < (nudge < 0 ? -nudge : nudge); ++j) a = nextafter(a, nudge < 0 ? 0.0 : INFINITY);
+        }
+        const double y = 1.0 / b;
+        if (oracle_invariant_div(a, b, y) != a / b) ++bad;
+    }
+    return bad;
+}

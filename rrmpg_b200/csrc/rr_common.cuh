@@ -324,12 +324,13 @@ __device__ __forceinline__ void stream_forcing_grouped(const double* __restrict_
 // Correctly rounded a / b for a loop-invariant b (Markstein): with y = RN(1/b) computed once by a real
 // division, q0 = RN(a y), and two residual corrections r = a - b q (exact in an FMA), q += r y, the
 // result equals the IEEE quotient RN(a/b) bit for bit when nothing under- or overflows (checked against
-// hardware division on 6e8 random and adversarial operand pairs, oracle-side).  The fast
+// hardware division on random and adversarial operand pairs by the oracle-side twin, tests/test_fastmath.py).  The fast
 // path is taken for a positive a with a mid-range exponent (one unsigned compare on its high word; span = 0
 // disables it, e.g. when b itself is out of range) and for a == +0; everything else -- negative, tiny, huge,
 // NaN -- uses the hardware division.  5 fp64 instructions instead of ~12 plus a slow-path call.
 // ----------------------------------------------------------------------------------------
-constexpr uint32_t kDivSpanOk = 0x7A400000u;  // exponents 2^-960 .. 2^+993
+constexpr uint32_t kDivSpanOk = 0x78000000u;  // exponents 2^-960 .. 2^+960: with b in [2^-60, 2^60] the quotient stays
+                                              // finite and normal (oracle_check_invariant_division, tests/test_fastmath.py)
 __device__ __forceinline__ uint32_t div_invariant_span(double b) {
     return (b >= 0x1p-60 && b <= 0x1p60) ? kDivSpanOk : 0u;
 }

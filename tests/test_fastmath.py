@@ -2,6 +2,7 @@
 import ctypes as C
 
 import numpy as np
+import pytest
 
 from rrmpg_b200 import _lib
 
@@ -233,3 +234,12 @@ def test_hbv_fast_step_algebra_matches_the_reference_recurrence():
     ref = oracle.hbvedu(f["temp"], f["prec"], m0, f["PE_m"], f["T_m"], (0, 100, 3, 10), P)
     assert np.allclose(q, ref, rtol=1e-10, atol=1e-12)
     assert np.max(np.abs(q - ref) / (np.abs(ref) + 1e-6)) < 1e-12
+
+
+@pytest.mark.parametrize("mode,n", [(0, 4_000_000), (1, 4_000_000), (2, 2_000_000)])
+def test_division_by_a_loop_invariant_is_the_ieee_quotient(mode, n):
+    """rr_common.cuh div_by_invariant / the Cemaneige contract step: the Markstein sequence (reciprocal computed once,
+    two FMA residual corrections) equals a / b bit for bit over the operand ranges the kernels admit without a
+    range check; restated in the oracle with exact fma()."""
+    import oracle
+    assert oracle.check_invariant_division(n, seed=12345 + mode, mode=mode) == 0
