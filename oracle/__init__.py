@@ -226,3 +226,14 @@ def mse_columns(qobs, qsim):
 def check_invariant_division(n, seed=1, mode=0):
     """Mismatches of the kernels' division-by-an-invariant sequence against IEEE division over n operand pairs."""
     return int(lib().oracle_check_invariant_division(int(n), int(seed), int(mode)))
+
+
+def cemaneige_contract_twin(prec, mean_temp, frac_solid, snow_pack_init, thermal_state_init, params):
+    """CPU twin of the CUDA contract snow step (test helper; see rr_oracle.c).  Returns (outflow, G, eTG)."""
+    prec = _f64(prec); mean_temp = _f64(mean_temp); frac_solid = _f64(frac_solid)
+    P = pack_params(params); (T, L), N = prec.shape, P.shape[0]
+    out, G, E = np.zeros((T, N)), np.zeros((T, L, N)), np.zeros((T, L, N))
+    lib().oracle_cemaneige_contract_twin(_d(prec), _d(mean_temp), _d(frac_solid), C.c_int64(T), C.c_int64(L),
+                                         C.c_double(snow_pack_init), C.c_double(thermal_state_init), _d(P),
+                                         C.c_int64(P.shape[1]), C.c_int64(N), _d(out), _d(G), _d(E))
+    return out, G, E

@@ -757,3 +757,52 @@ int64_t oracle_check_invariant_division(int64_t n, uint64_t seed, int mode)
     }
     return bad;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Test helper, not part of the reference: the CONTRACT step of the CUDA snow routine
+ * (rr_cemaneige.cuh, cema_kernel with CONTRACT = true) restated on the CPU with exact fma(), so that its
+ * bit-identity with run_cemaneige (oracle_cemaneige above) can be checked over long series and extreme
+ * in-contract parameters without a GPU: G / G_tresh evaluated unconditionally by the unchecked
+ * division-by-an-invariant sequence, potential melt and ratio by selects, mean over the layers by IEEE
+ * division.  outflow [T][N]; G, eTG [T][L][N] (nullable).  L <= 16.
+ * ------------------------------------------------------------------------------------------ */
+void oracle_cemaneige_contract_twin(const double *prec, const double *mean_temp, const double *frac, int64_t T,
+                                    int64_t L, double g0, double e0, const double *params, int64_t pstride,
+                                    int64_t N, double *outflow, double *Gout, double *Eout)
+{
+    double gt[16], inv_gt[16];
+    for (int64_t l = 0; l < L; ++l) {           /* the packer: snow = prec * frac, sequential mean */
+        double acc = 0.0;
+        for (int64_t t = 0; t < T; ++t) acc += prec[t * L + l] * frac[t * L + l];
+        gt[l] = 0.9 * 365.25 * (acc / (double)T);
+        inv_gt[l] = 1.0 / gt[l];
+    }
+    for (int64_t i = 0; i < N; ++i) {
+        const double CTG = params[i * pstride], Kf = params[i * pstride + 1];
+        const double omCTG = 1 - CTG;
+        double G[16], eTG[16];
+        for (int64_t t = 0; t < T; ++t) {
+            double lw_sum = 0.0;
+            for (int64_t l = 0; l < L; ++l) {
+                const double p = prec[t * L + l];
+                const double snow = p * frac[t * L + l], rain = p - snow, Tm = mean_temp[t * L + l];
+                double g = (t == 0) ? g0 : G[l] + snow;
+                double e = (t == 0) ? e0 : CTG * eTG[l] + omCTG * Tm;
+                e = (e > 0) ? 0.0 : e;
+                const double kt = Kf * Tm;
+                const double capped = (kt > g) ? g : kt;
+                const double pot = (e == 0 && Tm > 0) ? capped : 0.0;
+                const double q = oracle_invariant_div(g, gt[l], inv_gt[l]);
+                const double ratio = (g < gt[l]) ? q : 1.0;
+                const double melt = (0.9 * ratio + 0.1) * pot;
+                g = g - melt;
+                lw_sum += rain + melt;
+                G[l] = g;
+                eTG[l] = e;
+                if (Gout) Gout[(t * L + l) * N + i] = g;
+                if (Eout) Eout[(t * L + l) * N + i] = e;
+            }
+            outflow[t * N + i] = (L == 1) ? lw_sum : lw_sum / (double)L;
+        }
+    }
+}

@@ -243,3 +243,28 @@ def test_division_by_a_loop_invariant_is_the_ieee_quotient(mode, n):
     range check; restated in the oracle with exact fma()."""
     import oracle
     assert oracle.check_invariant_division(n, seed=12345 + mode, mode=mode) == 0
+
+
+def test_cemaneige_contract_step_twin_is_bit_identical_to_the_reference_routine():
+    """The contract step of cema_kernel (unconditional, unchecked G / G_tresh; selects for potential melt and ratio)
+    restated in C with exact fma() in the oracle library, against run_cemaneige's restatement: every bit of outflow, G and
+    eTG over long series, in-contract edge members (Kf = 0, CTG in {0, 1}, huge Kf, cold and warm starts) and packs that
+    decay towards zero over decades without snowfall."""
+    import oracle
+    from rrmpg_b200 import synthetic
+    from rrmpg_b200.models import Cemaneige, _snow_inputs
+    same = lambda a, b: np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(b).view(np.uint64))
+    for seed, T, alts, warm in ((1, 3000, [550, 620, 700, 785, 920], 0.0), (2, 1500, [], 0.0), (3, 2500, [1600, 2400, 3100], 0.0),
+                                (4, 14610, [500.0, 900.0], 25.0)):
+        f = synthetic.forcing(T, seed=100 + seed)
+        temp = f["temp"] + warm                     # warm = 25: it never snows, an initial pack melts away for 40 years
+        lp, lt, fr, _ = _snow_inputs.to_layers(f["prec"], temp, f["min_temp"] + warm, f["max_temp"] + warm, 480.0,
+                                               np.array(alts, dtype=float))
+        P = synthetic.random_params(Cemaneige(), 48, seed=200 + seed)
+        P["Kf"][:4] = [0.0, 1e-9, 1e3, 1e6]
+        P["CTG"][4:8] = [0.0, 1.0, 1e-12, 0.999999999]
+        for g0, e0 in ((0.0, 0.0), (35.0, -2.0), (1e-300, 0.0)):
+            ref = oracle.cemaneige(lp, lt, fr, g0, e0, P, return_storages=True)
+            got = oracle.cemaneige_contract_twin(lp, lt, fr, g0, e0, P)
+            for a, b, nm in zip(got, ref, ("outflow", "G", "eTG")):
+                assert same(a, b), f"seed {seed} g0={g0} {nm}"
