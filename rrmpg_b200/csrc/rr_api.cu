@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -237,6 +238,13 @@ struct Job {
 };
 
 static constexpr size_t kSlabTargetBytes = size_t(128) << 20;
+// device bytes of one chunk of catchments in the host-mode batch calls (two chunks are in flight); the environment
+// variable is a test knob that forces many small chunks through the ring
+static size_t multi_chunk_bytes() {
+    const char* e = getenv("RRMPG_B200_MULTI_CHUNK_BYTES");
+    const size_t v = e ? (size_t)strtoull(e, nullptr, 10) : 0;
+    return v > 0 ? v : kSlabTargetBytes * 2;
+}
 
 // Runs job.launch over [0, T).  Device mode: one launch straight into the caller's arrays.
 // Host mode: time slabs through a two-deep device ring; the D2H of slab k overlaps slab k+1.
@@ -433,7 +441,7 @@ static int run_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const std::ve
         if (o.ptr) bytes_per_catchment += o.per_catchment * (int64_t)sizeof(double);
     int64_t cc = C;
     if (bytes_per_catchment > 0)
-        cc = std::max<int64_t>(1, std::min<int64_t>(C, (int64_t)(kSlabTargetBytes * 2) / bytes_per_catchment));
+        cc = std::max<int64_t>(1, std::min<int64_t>(C, (int64_t)multi_chunk_bytes() / bytes_per_catchment));
     const int nchunks = (int)((C + cc - 1) / cc);
     std::vector<double*> dev[2] = {std::vector<double*>(no, nullptr), std::vector<double*>(no, nullptr)};
     int rc;
@@ -718,7 +726,7 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
     for (double* o : outs)
         if (o) bytes_per_catchment += T * N * (int64_t)sizeof(double);
     int64_t cc = C;
-    if (bytes_per_catchment > 0) cc = std::max<int64_t>(1, std::min<int64_t>(C, (int64_t)(kSlabTargetBytes * 2) / bytes_per_catchment));
+    if (bytes_per_catchment > 0) cc = std::max<int64_t>(1, std::min<int64_t>(C, (int64_t)multi_chunk_bytes() / bytes_per_catchment));
     const int nchunks = (int)((C + cc - 1) / cc);
     double* dev[2][5] = {};
     for (int sidx = 0; sidx < (nchunks > 1 ? 2 : 1); ++sidx)

@@ -61,7 +61,11 @@ __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double 
         if (qsim) qsim += c * batch.out_stride;
         if (s_store) { s_store += c * batch.out_stride; r_store += c * batch.out_stride; }
         if (obj.qobs) { obj.qobs += c * obj.T; obj.mse += c * N; }
-        if (batch.inits) { s_init = batch.inits[4 * c]; r_init = batch.inits[4 * c + 1]; }
+    }
+    if (batch.inits) {  // also for a batch (or a chunk of a batch) of ONE catchment
+        const int64_t c = batch.count > 1 ? (int64_t)blockIdx.y : 0;
+        s_init = batch.inits[4 * c];
+        r_init = batch.inits[4 * c + 1];
     }
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     // threads past the end of the ensemble recompute member N-1 and store the same values to the same

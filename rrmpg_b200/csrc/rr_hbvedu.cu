@@ -73,10 +73,11 @@ struct HbvOut {
             out.s1 += c * batch.out_stride; out.s2 += c * batch.out_stride;       \
         }                                                                         \
         if (obj.qobs) { obj.qobs += c * obj.T; obj.mse += c * N; }                \
-        if (batch.inits) {                                                        \
-            snow0 = batch.inits[4 * c]; soil0 = batch.inits[4 * c + 1];           \
-            s10 = batch.inits[4 * c + 2]; s20 = batch.inits[4 * c + 3];           \
-        }                                                                         \
+    }                                                                             \
+    if (batch.inits) { /* also for a batch (or a chunk of a batch) of ONE catchment */ \
+        const int64_t c = batch.count > 1 ? (int64_t)blockIdx.y : 0;              \
+        snow0 = batch.inits[4 * c]; soil0 = batch.inits[4 * c + 1];               \
+        s10 = batch.inits[4 * c + 2]; s20 = batch.inits[4 * c + 3];               \
     }
 
 struct HbvF {  // forcing of one timestep

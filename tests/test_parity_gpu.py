@@ -767,3 +767,33 @@ def test_abc_pair_kernel_and_scalar_kernel_are_bit_identical(N):
     both = engine.abc(f["prec"], 1.5, P, return_storage=True)
     assert_bits_equal(both["qsim"], ref[0], "abc qsim with storage")
     assert_bits_equal(both["storage"], ref[1], "abc storage")
+
+
+def test_multi_catchment_host_ring_with_many_small_chunks(monkeypatch):
+    """Host-mode catchment batches go through a two-deep device ring in chunks of catchments (D2H of chunk k overlaps
+    the kernel of chunk k+1).  The test knob RRMPG_B200_MULTI_CHUNK_BYTES forces one- and two-catchment chunks; results
+    must not depend on the chunking."""
+    Cn, T, N = 7, 300, 130
+    fs = [synthetic.forcing(T, seed=700 + c) for c in range(Cn)]
+    prec = np.stack([f["prec"] for f in fs]); etp = np.stack([f["etp"] for f in fs]); temp = np.stack([f["temp"] for f in fs])
+    m0 = np.stack([f["month"] - 1 for f in fs]).astype(np.int8)
+    PE = np.stack([f["PE_m"] for f in fs]); TM = np.stack([f["T_m"] for f in fs])
+    qobs = np.abs(np.random.default_rng(8).normal(1.0, 0.5, (Cn, T)))
+    Pg = np.stack([engine.pack_params(synthetic.random_params(GR4J(), N, seed=800 + c)) for c in range(Cn)])
+    Ph = np.stack([engine.pack_params(synthetic.random_params(HBVEdu(), N, seed=900 + c)) for c in range(Cn)])
+    run_g = lambda: engine.gr4j_multi(prec, etp, (0.6, 0.7), Pg, return_storage=True, qobs=qobs)
+    run_h = lambda: engine.hbvedu_multi(temp, prec, m0, PE, TM, (0, 100, 3, 10), Ph, return_storage=True, qobs=qobs)
+    monkeypatch.delenv("RRMPG_B200_MULTI_CHUNK_BYTES", raising=False)
+    whole_g, whole_h = run_g(), run_h()
+    # a batch of ONE catchment takes its initial states from the per-catchment array too
+    one = engine.gr4j_multi(prec[:1], etp[:1], (0.6, 0.7), Pg[:1])["qsim"][0]
+    assert_bits_equal(one, engine.gr4j(prec[0], etp[0], 0.6, 0.7, Pg[0])["qsim"], "gr4j_multi C=1")
+    one = engine.hbvedu_multi(temp[:1], prec[:1], m0[:1], PE[:1], TM[:1], (0, 100, 3, 10), Ph[:1])["qsim"][0]
+    assert_bits_equal(one, engine.hbvedu(temp[0], prec[0], m0[0], PE[0], TM[0], (0, 100, 3, 10), Ph[0])["qsim"], "hbvedu_multi C=1")
+    per_catchment = T * N * 8
+    for chunk in (per_catchment * 3, per_catchment * 5 * 2 + 1):   # GR4J: 3 outputs -> 1 catchment; HBV: 5 outputs -> 2
+        monkeypatch.setenv("RRMPG_B200_MULTI_CHUNK_BYTES", str(chunk))
+        for whole, run, tag in ((whole_g, run_g, "gr4j"), (whole_h, run_h, "hbvedu")):
+            got = run()
+            for nm in whole:
+                assert_bits_equal(got[nm], whole[nm], f"{tag} chunk={chunk} {nm}")
