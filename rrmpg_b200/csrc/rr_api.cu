@@ -22,7 +22,7 @@
 
 namespace rrb {
 
-static_assert(RRB_MATH_FAST == RRB_MATH_FAST_ && RRB_MATH_PRECISE == RRB_MATH_PRECISE_, "math enum mismatch");
+static_assert((int)RRB_MATH_FAST == (int)RRB_MATH_FAST_ && (int)RRB_MATH_PRECISE == (int)RRB_MATH_PRECISE_, "math enum mismatch");
 static_assert(RRB_MAX_LAYERS == kCemaMaxLayers, "layer cap mismatch");
 
 static thread_local std::string g_err;
@@ -283,7 +283,7 @@ static int run_job(Ctx& c, const Opts& o, const Job& job, const double* d_qobs, 
 
     double* state = nullptr;
     if (ring) {
-        void* p;
+        void* p = nullptr;
         int rc = c.ensure(B_STATE, sizeof(double) * (size_t)job.state_slots * (size_t)N, &p);
         if (rc) return rc;
         state = (double*)p;
@@ -293,7 +293,7 @@ static int run_job(Ctx& c, const Opts& o, const Job& job, const double* d_qobs, 
         dev[s].assign(nout, nullptr);
         for (int k = 0; k < nout; ++k) {
             if (!job.outs[k].user) continue;
-            void* p;
+            void* p = nullptr;
             int rc = c.ensure(B_OUT0 + 2 * k + s, sizeof(double) * (size_t)steps * (size_t)job.outs[k].row_elems, &p);
             if (rc) return rc;
             dev[s][k] = (double*)p;
@@ -331,7 +331,7 @@ static int stage_in(Ctx& c, const Opts& o, int slot, const T_* src, size_t count
         *out = src;
         return RRB_OK;
     }
-    void* p;
+    void* p = nullptr;
     int rc = c.ensure(slot, sizeof(T_) * count, &p);
     if (rc) return rc;
     RRB_CUDA(cudaMemcpyAsync(p, src, sizeof(T_) * count, cudaMemcpyHostToDevice, c.compute));
@@ -370,7 +370,7 @@ static int stage_common(Prepared* P, int64_t T, int64_t N, const double* params,
         if (P->o.mem == RRB_MEM_DEVICE) {
             P->d_mse = P->o.mse;
         } else {
-            void* p;
+            void* p = nullptr;
             rc = P->c->ensure(B_MSE, sizeof(double) * (size_t)std::max<int64_t>(N, 1), &p);
             if (rc) return rc;
             P->d_mse = (double*)p;
@@ -396,7 +396,7 @@ static int resolve_x4_max(Prepared* P, const double* host_or_dev_params, int64_t
         *out = P->o.x4_max;
         return RRB_OK;
     }
-    void* d;
+    void* d = nullptr;
     int rc = P->c->ensure(B_SCALAR, sizeof(double), &d);
     if (rc) return rc;
     max_field_kernel<<<1, 1024, 0, P->s>>>(P->d_params, N, stride, field, (double*)d);
@@ -448,7 +448,7 @@ static int run_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const std::ve
     for (int sidx = 0; sidx < (nchunks > 1 ? 2 : 1); ++sidx)
         for (int j = 0; j < no; ++j)
             if (outs[j].ptr) {
-                void* p;
+                void* p = nullptr;
                 if ((rc = c.ensure(B_OUT0 + 2 * j + sidx, sizeof(double) * (size_t)(cc * outs[j].per_catchment), &p))) return rc;
                 dev[sidx][j] = (double*)p;
             }
@@ -481,14 +481,14 @@ static int run_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const std::ve
 static int stage_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const double* inits4, const double** d_inits) {
     Ctx& c = *P.c;
     int rc;
-    void* di;
+    void* di = nullptr;
     if ((rc = c.ensure(B_SCALAR, sizeof(double) * 4 * (size_t)C, &di))) return rc;
     RRB_CUDA(cudaMemcpyAsync(di, inits4, sizeof(double) * 4 * (size_t)C, cudaMemcpyHostToDevice, P.s));
     *d_inits = (const double*)di;
     if (P.o.qobs) {
         if ((rc = stage_in(c, P.o, B_QOBS, P.o.qobs, (size_t)(C * T), &P.d_qobs))) return rc;
         if (P.o.mem == RRB_MEM_HOST) {
-            void* p;
+            void* p = nullptr;
             if ((rc = c.ensure(B_MSE, sizeof(double) * (size_t)(C * N), &p))) return rc;
             P.d_mse = (double*)p;
         } else {
@@ -604,7 +604,7 @@ int rrb_abc_simulate(const double* prec, int64_t T, double initial_state, const 
     const double* d_prec;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)T, &d_prec))) return rc;
     if ((rc = stage_common(&P, T, N, params, 3))) return rc;
-    void* F;
+    void* F = nullptr;
     if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)padded_steps(T, kAbcTT) * kAbcR, &F))) return rc;
     RRB_CUDA(pack_abc(d_prec, T, (double*)F, P.s));
     Job job;
@@ -641,7 +641,7 @@ int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* mo
     if ((rc = stage_common(&P, T, N, params, 11))) return rc;
     double in4[4];
     memcpy(in4, inits, sizeof(in4));  // inits is host memory in both modes
-    void* F;
+    void* F = nullptr;
     if ((rc = P.c->ensure(B_F, forcing_bytes(T, kHbvTT, kHbvR), &F))) return rc;
     RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.o.math, 1, P.s));
     Job job;
@@ -691,7 +691,7 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
     if (P.o.qobs) {
         if ((rc = stage_in(c, P.o, B_QOBS, P.o.qobs, (size_t)(C * T), &P.d_qobs))) return rc;
         if (host) {
-            void* p;
+            void* p = nullptr;
             if ((rc = c.ensure(B_MSE, sizeof(double) * (size_t)(C * N), &p))) return rc;
             P.d_mse = (double*)p;
         } else {
@@ -699,7 +699,7 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
         }
     }
     const int64_t Tpad = padded_steps(T, kHbvTT);
-    void* F;
+    void* F = nullptr;
     if ((rc = c.ensure(B_F, sizeof(double) * (size_t)(C * Tpad) * kHbvR + kForcingFlagBytes, &F))) return rc;
     RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.o.math, (int)C, P.s));
     const uint32_t* hbv_flag = reinterpret_cast<const uint32_t*>((const double*)F + C * Tpad * kHbvR);
@@ -732,7 +732,7 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
     for (int sidx = 0; sidx < (nchunks > 1 ? 2 : 1); ++sidx)
         for (int k = 0; k < 5; ++k)
             if (outs[k]) {
-                void* p;
+                void* p = nullptr;
                 if ((rc = c.ensure(B_OUT0 + 2 * k + sidx, sizeof(double) * (size_t)(cc * T * N), &p))) return rc;
                 dev[sidx][k] = (double*)p;
             }
@@ -783,7 +783,7 @@ int rrb_gr4j_simulate(const double* prec, const double* etp, int64_t T, double s
     if (!(x4_max <= RRB_MAX_X4))
         return fail(RRB_EUNSUPPORTED, "GR4J x4 up to %g in this batch; the unit hydrograph buffers support x4 <= %g",
                     x4_max, RRB_MAX_X4);
-    void* F;
+    void* F = nullptr;
     if ((rc = P.c->ensure(B_F, forcing_bytes(T, kGr4jTT, kGr4jR), &F))) return rc;
     RRB_CUDA(pack_gr4j(d_prec, d_etp, T, (double*)F, P.s));
     Job job;
@@ -819,7 +819,7 @@ int rrb_cemaneige_simulate(const double* prec, const double* mean_temp, const do
     if ((rc = stage_in(*P.c, P.o, B_RAW2, frac_solid, (size_t)(T * L), &d_fr))) return rc;
     if ((rc = stage_common(&P, T, N, params, param_stride))) return rc;
     const int LC = cema_layer_class((int)L);
-    void *F, *gt;
+    void *F = nullptr, *gt = nullptr;
     if ((rc = P.c->ensure(B_F, forcing_bytes(T, cema_TT(LC), cema_R(LC)), &F))) return rc;
     if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers, &gt))) return rc;
     RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, nullptr, T, (int)L, (double*)F, (double*)gt, P.s));
@@ -865,7 +865,7 @@ int rrb_cemaneigegr4j_simulate(const double* prec, const double* mean_temp, cons
         return fail(RRB_EUNSUPPORTED, "GR4J x4 up to %g in this batch; the unit hydrograph buffers support x4 <= %g",
                     x4_max, RRB_MAX_X4);
     const int LC = cema_layer_class((int)L);
-    void *F, *gt;
+    void *F = nullptr, *gt = nullptr;
     if ((rc = P.c->ensure(B_F, forcing_bytes(T, cema_TT(LC), cema_R(LC)), &F))) return rc;
     if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers, &gt))) return rc;
     RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, d_etp, T, (int)L, (double*)F, (double*)gt, P.s));
@@ -919,7 +919,7 @@ static int snowice_simulate(int family, const double* prec, const double* mean_t
         return fail(RRB_EUNSUPPORTED, "GR4J x4 up to %g in this batch; the unit hydrograph buffers support x4 <= %g",
                     x4_max, RRB_MAX_X4);
     const int LC = cema_layer_class((int)L);
-    void *F, *gt;
+    void *F = nullptr, *gt = nullptr;
     if ((rc = P.c->ensure(B_F, forcing_bytes(T, cema_TT(LC), cema_R(LC)), &F))) return rc;
     if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers, &gt))) return rc;
     RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, d_etp, T, (int)L, (double*)F, (double*)gt, P.s));
@@ -997,7 +997,7 @@ int rrb_gr4j_simulate_multi(const double* prec, const double* etp, int64_t C, in
     if ((rc = stage_multi(P, C, T, N, in4.data(), &d_inits))) return rc;
     RRB_CUDA(cudaStreamSynchronize(P.s));  // in4 is a temporary
     const int64_t fstride = forcing_stride_flagged(T, kGr4jTT, kGr4jR);
-    void* F;
+    void* F = nullptr;
     if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)(C * fstride), &F))) return rc;
     RRB_CUDA(pack_gr4j(d_prec, d_etp, T, (double*)F, P.s, (int)C));
     const double* dp = P.d_params;
@@ -1042,7 +1042,7 @@ int rrb_cemaneigegr4j_simulate_multi(const double* prec, const double* mean_temp
     RRB_CUDA(cudaStreamSynchronize(P.s));  // the caller's inits array may be a temporary
     const int LC = cema_layer_class((int)L);
     const int64_t fstride = forcing_stride_flagged(T, cema_TT(LC), cema_R(LC));
-    void *F, *gt;
+    void *F = nullptr, *gt = nullptr;
     if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)(C * fstride), &F))) return rc;
     if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers * (size_t)C, &gt))) return rc;
     RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, d_etp, T, (int)L, (double*)F, (double*)gt, P.s, (int)C));
@@ -1090,7 +1090,7 @@ int rrb_snow_layers(const double* prec, const double* mean_temp, const double* m
     double* outs_d[3] = {layer_prec, layer_mean_temp, frac_solid};
     if (host)
         for (int j = 0; j < 3; ++j) {
-            void* p;
+            void* p = nullptr;
             if ((rc = P.c->ensure(B_OUT0 + j, bytes, &p))) return rc;
             outs_d[j] = (double*)p;
         }
