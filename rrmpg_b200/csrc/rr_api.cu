@@ -348,6 +348,19 @@ struct Prepared {
     double* d_mse = nullptr;
 };
 
+// Host mode hands the caller's buffers to asynchronous copies.  Whatever path leaves an entry point (an error return
+// in the middle of the prologue or of the slab ring included), nothing may still be reading or writing caller memory:
+// the guard drains both context streams on scope exit (a no-op after a successful run_job, which has synchronised).
+struct HostDrain {
+    const Prepared& P;
+    ~HostDrain() {
+        if (P.c && P.o.mem == RRB_MEM_HOST) {
+            (void)cudaStreamSynchronize(P.c->compute);
+            (void)cudaStreamSynchronize(P.c->copy);
+        }
+    }
+};
+
 static int prepare(const rrb_opts* opts, int64_t T, int64_t N, const double* params, int64_t pwidth, Prepared* P) {
     int rc = parse_opts(opts, &P->o);
     if (rc) return rc;
@@ -601,6 +614,7 @@ int rrb_abc_simulate(const double* prec, int64_t T, double initial_state, const 
     if (!qsim && !P.o.qobs) return fail(RRB_EINVAL, "nothing to compute: qsim is NULL and no objective requested");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain{P};
     const double* d_prec;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)T, &d_prec))) return rc;
     if ((rc = stage_common(&P, T, N, params, 3))) return rc;
@@ -631,6 +645,7 @@ int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* mo
     if (!qsim && !P.o.qobs && nst == 0) return fail(RRB_EINVAL, "nothing to compute");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain{P};
     const double *d_temp, *d_prec, *d_pe, *d_tm;
     const int8_t* d_month;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, temp, (size_t)T, &d_temp))) return rc;
@@ -674,6 +689,7 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
     if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
     if (N == 0 || C == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain{P};
     Ctx& c = *P.c;
     const bool host = P.o.mem == RRB_MEM_HOST;
     const double *d_temp, *d_prec, *d_pe, *d_tm;
@@ -774,6 +790,7 @@ int rrb_gr4j_simulate(const double* prec, const double* etp, int64_t T, double s
     if (!qsim && !P.o.qobs && !s_store) return fail(RRB_EINVAL, "nothing to compute");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain{P};
     const double *d_prec, *d_etp;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)T, &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, etp, (size_t)T, &d_etp))) return rc;
@@ -813,6 +830,7 @@ int rrb_cemaneige_simulate(const double* prec, const double* mean_temp, const do
     if (!outflow && !P.o.qobs && !G) return fail(RRB_EINVAL, "nothing to compute");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain{P};
     const double *d_prec, *d_mt, *d_fr;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(T * L), &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(T * L), &d_mt))) return rc;
@@ -851,6 +869,7 @@ int rrb_cemaneigegr4j_simulate(const double* prec, const double* mean_temp, cons
     if (!qsim && !P.o.qobs && nst == 0) return fail(RRB_EINVAL, "nothing to compute");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain{P};
     const double *d_prec, *d_mt, *d_fr, *d_etp;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(T * L), &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(T * L), &d_mt))) return rc;
@@ -902,6 +921,7 @@ static int snowice_simulate(int family, const double* prec, const double* mean_t
     if (!o.qsim && !P.o.qobs && n_storage_given == 0) return fail(RRB_EINVAL, "nothing to compute");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain{P};
     const double *d_prec, *d_mt, *d_fr, *d_etp, *d_fice = nullptr;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(T * L), &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(T * L), &d_mt))) return rc;
@@ -982,6 +1002,7 @@ int rrb_gr4j_simulate_multi(const double* prec, const double* etp, int64_t C, in
     if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
     if (N == 0 || C == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain{P};
     const double *d_prec, *d_etp, *d_inits;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(C * T), &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, etp, (size_t)(C * T), &d_etp))) return rc;
@@ -1027,6 +1048,7 @@ int rrb_cemaneigegr4j_simulate_multi(const double* prec, const double* mean_temp
     if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
     if (N == 0 || C == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain{P};
     const double *d_prec, *d_mt, *d_fr, *d_etp, *d_inits;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(C * T * L), &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(C * T * L), &d_mt))) return rc;
@@ -1079,6 +1101,7 @@ int rrb_snow_layers(const double* prec, const double* mean_temp, const double* m
         k.high[l] = (flags[l] & RRB_LAYER_HIGH) != 0;
     }
     std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain{P};
     const double *d_p, *d_me, *d_mn, *d_mx;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)T, &d_p))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)T, &d_me))) return rc;
