@@ -31,6 +31,26 @@ __global__ void dadd_chain(double* out, double a, int iters, long long* cycles) 
     if (threadIdx.x == 0) *cycles = t1 - t0;
 }
 
+// Half-masked warps: only lanes [0, active) run the chain (the others leave through the early return, so the warp
+// issues every DFMA with a partial active mask).  If the 16-lane fp64 pipe skips the pass of an all-inactive half
+// warp, 16 active lanes cost one issue slot instead of two -- the premise of the "half-masked tail warps" remedy for
+// the 65 536-member load imbalance.
+template <int ILP>
+__global__ void dfma_chain_masked(double* out, double a, double b, int iters, int active) {
+    if ((int)(threadIdx.x & 31) >= active) return;
+    double x[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) x[k] = a + k + threadIdx.x;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) x[k] = fma(x[k], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) s += x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main() {
     double* out; long long* cyc; long long h;
     cudaMalloc(&out, sizeof(double) * 148 * 1024 * 8);
@@ -72,6 +92,18 @@ int main() {
         double dfma = (double)sms * threads * iters;
         printf("%2d warps/SMSP ILP1: %.2f TDFMA/s, %.3f DFMA/clk/SM\n", wps, dfma / ms / 1e9,
                dfma / (ms * 1e-3) / sms / 1.965e9);
+    }
+    // issue cost of partially active warps: 4 warps per sub-partition, ILP 4 (issue bound), warp-instructions per clock
+    for (int active : {32, 24, 17, 16, 8, 1}) {
+        const int threads = 4 * 4 * 32;
+        dfma_chain_masked<4><<<sms, threads>>>(out, 1.0000001, 1e-9, 1024, active);
+        cudaEventRecord(e0);
+        dfma_chain_masked<4><<<sms, threads>>>(out, 1.0000001, 1e-9, iters, active);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double winst = (double)sms * (threads / 32) * iters * 4;
+        printf("%2d active lanes per warp: %.3f warp-DFMA/clk/SMSP @1.965GHz (0.5 = two passes per instruction)\n", active,
+               winst / (ms * 1e-3) / sms / 4 / 1.965e9);
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
