@@ -87,7 +87,8 @@ typedef struct rrb_opts {
     void* stream;        /* RRB_MEM_DEVICE: cudaStream_t the work is enqueued on (NULL = default stream);
                             the call returns without synchronising */
     int32_t block;       /* threads per CTA, 0 = chosen from N and the SM count */
-    int32_t reserved;
+    int32_t variant;     /* kernel variant, for A/B timing only: 0 = the library's choice.  HBV-Edu FAST: 1 = one member per
+                            thread, 2 = two members per thread (needs an even N and 16-byte aligned rows, else 1) */
     double x4_max;       /* RRB_MEM_DEVICE, GR4J family: max x4 over params if the caller knows it;
                             <= 0 lets the library reduce it on the device (one small sync) */
     const double* qobs;  /* optional [T] observed discharge: fuses the objective into the kernel */
@@ -226,6 +227,10 @@ RRB_API int rrb_snow_layers(const double* prec, const double* mean_temp, const d
 /* ---- host-side checks of the FAST math (no GPU needed; used by the CPU test-suite) ------- */
 RRB_API void rrb_host_fast_pow(const double* x, const double* y, int64_t n, double* out);
 RRB_API void rrb_host_fast_exp2m1(const double* z, int64_t n, double* out);
+/* the soil-chain step of the HBV-Edu FAST kernel (rr_math.cuh, hbv_pow_step_twin): prec_eff = liquid (soil/FC)^Beta
+ * (rrmpg/models/hbvedu_model.py:99) and soil_new = soil_partial - prec_eff, same operation sequence as the device code */
+RRB_API void rrb_host_hbv_pow_step(const double* soil, const double* FC, const double* Beta, const double* liquid,
+                                   const double* soil_partial, int64_t n, double* prec_eff, double* soil_new);
 
 #ifdef __cplusplus
 }

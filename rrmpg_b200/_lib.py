@@ -26,7 +26,7 @@ class Opts(C.Structure):
     """``struct rrb_opts`` (include/rrmpg_b200.h)."""
     _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("mem", C.c_int32),
                 ("math", C.c_int32), ("stream", C.c_void_p), ("block", C.c_int32),
-                ("reserved", C.c_int32), ("x4_max", C.c_double), ("qobs", C.c_void_p),
+                ("variant", C.c_int32), ("x4_max", C.c_double), ("qobs", C.c_void_p),
                 ("mse", C.c_void_p), ("slab_steps", C.c_int64)]
 
 
@@ -68,6 +68,7 @@ _SIGS = {
     "rrb_snow_layers": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int64] + [C.c_void_p] * 6 + [C.POINTER(Opts)]),
     "rrb_host_fast_pow": (None, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "rrb_host_fast_exp2m1": (None, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "rrb_host_hbv_pow_step": (None, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -190,7 +190,7 @@ static int get_ctx(int device, Ctx** out) {
 }
 
 struct Opts {
-    int device = -1, mem = RRB_MEM_HOST, math = RRB_MATH_FAST, block = 0;
+    int device = -1, mem = RRB_MEM_HOST, math = RRB_MATH_FAST, block = 0, variant = 0;
     cudaStream_t stream = nullptr;
     double x4_max = 0.0;
     const double* qobs = nullptr;
@@ -212,6 +212,7 @@ static int parse_opts(const rrb_opts* o, Opts* out) {
     out->mem = o->mem;
     out->math = o->math;
     out->block = o->block;
+    out->variant = o->variant;
     out->stream = (cudaStream_t)o->stream;
     out->x4_max = o->x4_max;
     out->qobs = o->qobs;
@@ -255,6 +256,7 @@ static int run_job(Ctx& c, const Opts& o, const Job& job, const double* d_qobs, 
     cfg.block = o.block;
     cfg.math = o.math;
     cfg.sm_count = c.sm_count;
+    cfg.variant = o.variant;
     Objective obj{d_qobs, d_mse, T};
 
     if (o.mem == RRB_MEM_DEVICE) {
@@ -440,6 +442,7 @@ static int run_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const std::ve
     cfg.block = P.o.block;
     cfg.math = P.o.math;
     cfg.sm_count = c.sm_count;
+    cfg.variant = P.o.variant;
     cfg.stream = P.s;
     const int no = (int)outs.size();
     std::vector<double*> ptrs(no);
@@ -657,7 +660,7 @@ int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* mo
     double in4[4];
     memcpy(in4, inits, sizeof(in4));  // inits is host memory in both modes
     void* F = nullptr;
-    if ((rc = P.c->ensure(B_F, forcing_bytes(T, kHbvTT, kHbvR), &F))) return rc;
+    if ((rc = P.c->ensure(B_F, forcing_bytes(T, kHbvTT, kHbvR) + hbv_scratch_bytes(N, 1), &F))) return rc;
     RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.o.math, 1, P.s));
     Job job;
     job.T = T; job.N = N;
@@ -716,7 +719,7 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
     }
     const int64_t Tpad = padded_steps(T, kHbvTT);
     void* F = nullptr;
-    if ((rc = c.ensure(B_F, sizeof(double) * (size_t)(C * Tpad) * kHbvR + kForcingFlagBytes, &F))) return rc;
+    if ((rc = c.ensure(B_F, sizeof(double) * (size_t)(C * Tpad) * kHbvR + hbv_scratch_bytes(N, C), &F))) return rc;
     RRB_CUDA(pack_hbvedu(d_temp, d_prec, d_month, d_pe, d_tm, T, (double*)F, P.o.math, (int)C, P.s));
     const uint32_t* hbv_flag = reinterpret_cast<const uint32_t*>((const double*)F + C * Tpad * kHbvR);
 
@@ -724,6 +727,7 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
     cfg.block = P.o.block;
     cfg.math = P.o.math;
     cfg.sm_count = c.sm_count;
+    cfg.variant = P.o.variant;
     cfg.stream = P.s;
     const double zero4[4] = {0, 0, 0, 0};
     double* outs[5] = {qsim, snow, soil, s1, s2};
@@ -1128,6 +1132,11 @@ int rrb_snow_layers(const double* prec, const double* mean_temp, const double* m
 
 void rrb_host_fast_pow(const double* x, const double* y, int64_t n, double* out) {
     for (int64_t i = 0; i < n; ++i) out[i] = fast_pow(x[i], y[i], &h_fast_tables);
+}
+void rrb_host_hbv_pow_step(const double* soil, const double* FC, const double* Beta, const double* liquid,
+                           const double* soil_partial, int64_t n, double* prec_eff, double* soil_new) {
+    for (int64_t i = 0; i < n; ++i)
+        prec_eff[i] = hbv_pow_step_twin(soil[i], log2(FC[i]), Beta[i], liquid[i], soil_partial[i], &h_hbv_tables, &soil_new[i]);
 }
 void rrb_host_fast_exp2m1(const double* z, int64_t n, double* out) {
     for (int64_t i = 0; i < n; ++i) out[i] = fast_exp2m1_nonneg(z[i], &h_fast_tables);

@@ -69,6 +69,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // streaming (evict-first) stores of the output rows
 __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+// two neighbouring members of one output row in one 16-byte streaming store (p 16-byte aligned)
+__device__ __forceinline__ void st_stream_pair(double* p, double x, double y) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory");
+}
 
 // numba's lowering of Python max(0, x) / min(a, b) on floats (oracle/rr_oracle.c header):
 // max(0, x) = (x > 0) ? x : 0.0 (so max(0, NaN) = 0), min(a, b) = (b < a) ? b : a.

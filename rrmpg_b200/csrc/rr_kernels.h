@@ -34,6 +34,7 @@ struct LaunchCfg {
     int block;  // threads per CTA (0 = auto from N and the SM count)
     int math;   // RRB_MATH_FAST / RRB_MATH_PRECISE
     int sm_count;
+    int variant;  // rrb_opts.variant (0 = default)
 };
 
 // fused per-member objective: when qobs != nullptr the kernels accumulate
@@ -70,6 +71,11 @@ inline size_t forcing_bytes(int64_t T, int TT, int R) {
 template <class D>
 inline uint32_t* forcing_flag(D* F, int64_t T, int TT, int R) {
     return reinterpret_cast<uint32_t*>(const_cast<double*>(F) + padded_steps(T, TT) * R);
+}
+// HBV-Edu scratch behind the packed forcing of `count` catchments: the forcing flag slot, then one flag word per CTA of
+// the FAST launch ("leave this CTA's members to the PRECISE kernel": rr_hbvedu.cu).  A CTA covers at least 32 members.
+inline size_t hbv_scratch_bytes(int64_t N, int64_t count) {
+    return kForcingFlagBytes + sizeof(uint32_t) * (size_t)(((N + 31) / 32) * count) + 16;
 }
 // catchment batches of these models: every catchment's block is followed by its own flag slot
 inline int64_t forcing_stride_flagged(int64_t T, int TT, int R) {

@@ -279,6 +279,80 @@ __device__ __forceinline__ double pow35_sane(double w, const Exp2Regs& k) {
     return (w2 * w2) * y;
 }
 
+// ----------------------------------------------------------------------------------------
+// Round 2: the HBV-Edu soil chain.  prec_eff = liquid (soil/FC)^Beta (rrmpg/models/hbvedu_model.py:99) sits on the
+// only long loop-carried dependency of the model (soil -> log2 -> x Beta -> exp2 -> soil); with 3.5 warps per SM
+// sub-partition at 65 536 members the kernel runs at the latency of that chain, not at an issue or pipe limit
+// (profiles/r02_fp64_probe.txt).  The sequence below is organised for DEPTH:
+//   * log2(soil/FC) = log2(soil) - log2(FC) with the second term hoisted (one DMUL off the chain),
+//   * 512-entry log2 table indexed by the top mantissa bits (|r| < 2^-10: degree 4 instead of 6, Estrin depth 2),
+//   * kd = fma(Beta, L, shift) / r = fma(Beta, L, -(kd - shift)): the product Beta L is never rounded on its own,
+//   * 1024-entry exp2 table (|r| <= 2^-11: (2^r - 1)/r at degree 2),
+//   * the table scale 2^(k/1024) arrives late (LDS behind the shift), so it enters last:
+//     w = liquid (1 + r g) first, then soil_new = fma(-scale, w, soil_partial) and prec_eff = scale w side by side.
+// Host/device twin of the exact device sequence (tests/test_fastmath.py checks it against glibc pow on the CPU).
+// ----------------------------------------------------------------------------------------
+namespace hbvpow {
+// log2(1 + r) / r = A1 + A2 r + A3 r^2 + A4 r^3 (|r| < 2^-10: the r^5 term is below 2^-51.8 absolute)
+constexpr double A1 = 0x1.71547652b82fep+0, A2 = -0x1.71547652b82fep-1, A3 = 0x1.ec709dc3a03fdp-2, A4 = -0x1.71547652b82fep-2;
+// (2^r - 1) / r = C1 + C2 r + C3 r^2 (|r| <= 2^-11: the r^4 term is below 5.5e-16 relative)
+constexpr double C1 = 0x1.62e42fefa39efp-1, C2 = 0x1.ebfbdff82c58fp-3, C3 = 0x1.c6b08d704a0c0p-5;
+constexpr double kShift = 0x1.8p52 / tables::kExpKN;  // rounds to multiples of 1/1024
+}  // namespace hbvpow
+struct HbvTables {
+    double log2m[2 * tables::kLogMN];           // {invc, log2c}, index = top 9 mantissa bits
+    unsigned long long exp2k[tables::kExpKN];   // bits(2^(j/1024)) - (j << 42)
+    double poly[8];                             // A1..A4, C1..C3: read back through volatile shared loads so that the
+                                                // assembler keeps them in registers instead of re-materialising them
+};
+#define RRB_HBV_POLY {hbvpow::A1, hbvpow::A2, hbvpow::A3, hbvpow::A4, hbvpow::C1, hbvpow::C2, hbvpow::C3, 0.0}
+#ifdef __CUDACC__
+static __device__ const HbvTables d_hbv_tables = {RRB_LOG2M_TABLE, RRB_EXP2K_TABLE, RRB_HBV_POLY};
+#endif
+static const HbvTables h_hbv_tables = {RRB_LOG2M_TABLE, RRB_EXP2K_TABLE, RRB_HBV_POLY};
+
+// liquid * (soil/FC)^Beta and the new soil moisture soil_partial - that, for a positive normal soil with
+// soil/FC in [2^-15, 2^15), |Beta| < 32, log2FC = log2(FC).  Returns prec_eff; *soil_new = fma(-scale, w, soil_partial).
+__host__ __device__ __forceinline__ double hbv_pow_step_twin(double soil, double log2FC, double Beta, double liquid,
+                                                            double soil_partial, const HbvTables* tb, double* soil_new) {
+    using namespace hbvpow;
+    const uint64_t ix = f64_bits(soil);
+    const uint32_t hs = (uint32_t)(ix >> 32);
+    const int i = (int)((hs >> 11) & (tables::kLogMN - 1));
+    const double m = bits_f64((ix & 0x000FFFFFFFFFFFFFULL) | 0x3FF0000000000000ULL);
+    const double kml = (double)((int)(hs >> 20) - 1023) - log2FC;
+    const double invc = tb->log2m[2 * i], log2c = tb->log2m[2 * i + 1];
+    const double r = fma(m, invc, -1.0);
+    const double base = kml + log2c;
+    const double r2 = r * r;
+    const double a = fma(r, A2, A1);
+    const double b = fma(r, A4, A3);
+    const double t = fma(r2, b, a);
+    const double L = fma(r, t, base);                 // log2(soil / FC)
+    const double kd = fma(Beta, L, kShift);
+    const uint32_t ki = (uint32_t)f64_bits(kd);       // round(1024 Beta L), two's complement
+    const double kdm = kd - kShift;
+    const double rr = fma(Beta, L, -kdm);             // |rr| <= 2^-11
+    const double scale = bits_f64(tb->exp2k[ki & (tables::kExpKN - 1)] + ((uint64_t)ki << 42));
+    const double q2 = rr * rr;
+    const double e = fma(rr, C2, C1);
+    const double g = fma(q2, C3, e);
+    const double u = rr * g;                          // 2^rr - 1
+    const double w = fma(liquid, u, liquid);          // liquid 2^rr
+    *soil_new = fma(-scale, w, soil_partial);
+    return scale * w;
+}
+
+// stage the HBV tables into shared memory (call by every thread, before a __syncthreads())
+__device__ __forceinline__ const HbvTables* hbv_tables_to_smem(unsigned char* smem_at) {
+    HbvTables* dst = reinterpret_cast<HbvTables*>(smem_at);
+    const double2* src = reinterpret_cast<const double2*>(&d_hbv_tables);
+    double2* d = reinterpret_cast<double2*>(dst);
+    for (int k = threadIdx.x; k < (int)(sizeof(HbvTables) / 16); k += blockDim.x) d[k] = src[k];
+    return dst;
+}
+__host__ __device__ constexpr size_t hbv_tables_smem_bytes() { return sizeof(HbvTables); }
+
 // stage the tables into shared memory (call by every thread, before a __syncthreads())
 __device__ __forceinline__ const FastTables* fastmath_tables_to_smem(unsigned char* smem_at) {
     FastTables* dst = reinterpret_cast<FastTables*>(smem_at);

@@ -25,6 +25,7 @@ _MATH = {"fast": _lib.MATH_FAST, "precise": _lib.MATH_PRECISE,
          _lib.MATH_FAST: _lib.MATH_FAST, _lib.MATH_PRECISE: _lib.MATH_PRECISE}
 
 DEFAULT_MATH = "fast"
+VARIANT = 0  # rrb_opts.variant of every call made through this module (kernel A/B timing and variant parity tests)
 
 
 def _is_torch(a):
@@ -58,6 +59,7 @@ class _Call:
         self.opts.math = _MATH[math]
         self.opts.block = int(block)
         self.opts.slab_steps = int(slab_steps)
+        self.opts.variant = int(VARIANT)
         self.opts.x4_max = float(x4_max)
         self.keep = []
         if self.torch_mode:

@@ -26,6 +26,44 @@ def test_fast_pow_accuracy_on_the_hbv_operand_range():
     assert rel.max() < 4e-15 and rel.mean() < 2.5e-16
 
 
+def _hbv_pow_step(soil, FC, Beta, liquid, sp):
+    a = [np.ascontiguousarray(v, np.float64) for v in (soil, FC, Beta, liquid, sp)]
+    pe = np.empty_like(a[0]); sn = np.empty_like(a[0])
+    _lib.lib().rrb_host_hbv_pow_step(*[v.ctypes.data for v in a], a[0].size, pe.ctypes.data, sn.ctypes.data)
+    return pe, sn
+
+
+def test_hbv_soil_chain_step_twin_vs_libm():
+    """Round-2 soil chain (rr_math.cuh hbv_pow_step_twin = the device sequence of hbv_fast2_kernel): hoisted log2(FC),
+    512-entry log2 / 1024-entry exp2 tables, fused shift, late table scale.  prec_eff = liquid (soil/FC)^Beta within
+    8e-15 relative of glibc over the default bounds (hbvedu.py:47-60), 1e-13 over the whole admitted range
+    soil/FC in [2^-15, 2^15), |Beta| < 32; soil_new = soil_partial - prec_eff to the rounding of that subtraction."""
+    rng = np.random.default_rng(11)
+    n = 400_000
+    FC = rng.uniform(100, 200, n); Beta = rng.uniform(1, 7, n)
+    soil = FC * rng.uniform(0.05, 1.5, n); liquid = rng.gamma(0.8, 6.0, n); sp = soil + liquid
+    pe, sn = _hbv_pow_step(soil, FC, Beta, liquid, sp)
+    ref = liquid * np.power(soil / FC, Beta)
+    rel = np.abs(pe - ref) / ref
+    assert rel.max() < 8e-15 and rel.mean() < 1e-15, (rel.max(), rel.mean())  # incl. the rounding of soil/FC itself (x Beta)
+    assert np.max(np.abs(sn - (sp - ref)) / np.abs(sp)) < 4e-15
+    # the whole admitted operand range
+    FC = 10 ** rng.uniform(-3, 6, n); Beta = rng.uniform(-31.9, 31.9, n)
+    soil = FC * 2 ** rng.uniform(-14.99, 14.99, n)
+    pe, sn = _hbv_pow_step(soil, FC, Beta, np.ones(n), np.zeros(n))
+    ref = np.power(soil / FC, Beta)
+    assert np.all(np.isfinite(pe)) and (np.abs(pe - ref) / ref).max() < 1e-13
+    assert np.array_equal(sn, -pe)  # fma(-scale, w, 0) = -(scale w)
+    # mantissa-bin and table-index edges: soil at powers of two and just below them, soil == FC
+    FC = np.full(8, 150.0); soil = np.array([128.0, np.nextafter(128.0, 0), 256.0, np.nextafter(256.0, 0), 150.0, 64.0, 1.0, 1e-2])
+    pe, _ = _hbv_pow_step(soil, FC, np.full(8, 3.3), np.ones(8), np.zeros(8))
+    ref = np.power(soil / FC, 3.3)
+    assert (np.abs(pe - ref) / ref).max() < 4e-15
+    # no liquid water: prec_eff is +0 and the soil moisture passes through
+    pe, sn = _hbv_pow_step([120.0], [150.0], [2.0], [0.0], [119.5])
+    assert pe[0] == 0.0 and sn[0] == 119.5
+
+
 def test_fast_pow_accuracy_wide_range():
     rng = np.random.default_rng(1)
     x = 10 ** rng.uniform(-6, 6, 400_000); y = rng.uniform(-9, 9, 400_000)

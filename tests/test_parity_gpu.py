@@ -797,3 +797,82 @@ def test_multi_catchment_host_ring_with_many_small_chunks(monkeypatch):
             got = run()
             for nm in whole:
                 assert_bits_equal(got[nm], whole[nm], f"{tag} chunk={chunk} {nm}")
+
+
+# ------------------------------------------------------------------ round 2: HBV-Edu FAST kernel variants
+@pytest.fixture
+def hbv_variant():
+    """Sets rrb_opts.variant for the calls of one test (1 / 2: hbv_fast2_kernel with one / two members per thread,
+    3: the round-1 kernel) and restores the library default afterwards."""
+    def set_variant(v):
+        engine.VARIANT = v
+    yield set_variant
+    engine.VARIANT = 0
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("N", [70, 71, 1000])
+def test_hbvedu_fast_kernel_variants_vs_oracle(variant, N, hbv_variant):
+    hbv_variant(variant)
+    T = 700
+    f, P = _hbv_case(T, N, seed=21)
+    qobs = np.abs(np.random.default_rng(5).normal(2.0, 1.0, T))
+    args = (f["temp"], f["prec"], f["month"] - 1, f["PE_m"], f["T_m"], (2.0, 100, 3, 10), P)
+    ref = oracle.hbvedu(*args, return_storage=True)
+    got = engine.hbvedu(*args, return_storage=True, qobs=qobs)
+    for nm, r in zip(["qsim", "snow", "soil", "s1", "s2"], ref):
+        assert_close(got[nm], r, f"variant {variant} N={N} {nm}")
+    assert_close(got["mse"], np.mean((qobs[:, None] - ref[0]) ** 2, axis=0), f"variant {variant} mse", rtol=1e-9)
+    q_only = engine.hbvedu(*args)["qsim"]
+    assert_bits_equal(q_only, got["qsim"], f"variant {variant}: discharge-only launch vs all outputs")
+    sl = engine.hbvedu(*args, return_storage=True, qobs=qobs, slab_steps=97)
+    for nm in got:
+        assert_bits_equal(sl[nm], got[nm], f"variant {variant}: time slabs {nm}")
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_hbvedu_members_outside_the_fast_contract_fall_back_per_cta(variant, hbv_variant):
+    """hbv_fast2_kernel has no range check and no slow path in its time loop: members outside its contract (decided
+    before the loop) and members whose soil moisture leaves the range of the table-driven pow (sticky maximum, judged
+    after the loop) flag their CTA, whose members the PRECISE kernel queued behind then simulates -- slab by slab,
+    with the carry state handed back and forth between the two kernels."""
+    hbv_variant(variant)
+    T, N = 600, 1000
+    f, P = _hbv_case(T, N, seed=33)
+    P["FC"][5] = 1e-200          # outside [2^-500, 2^500]
+    P["Beta"][70] = 40.0         # |Beta| >= 32
+    P["PWP"][200] = 0.0
+    P["K_0"][333] = np.inf
+    P["FC"][450] = 3.5e6         # soil/FC below 2^-15 from the first step on
+    P["FC"][777] = 1.0e6         # ... and here only after a dry spell (range exit in the middle of the series)
+    P["FC"][999] = -150.0        # negative base of the pow: NaN from the first wet step on
+    for prec in (f["prec"], np.zeros(T)):
+        args = (f["temp"], prec, f["month"] - 1, f["PE_m"], f["T_m"], (0.0, 100, 3, 10), P)
+        with np.errstate(all="ignore"):
+            ref = oracle.hbvedu(*args, return_storage=True)
+        for slab in (0, 128):
+            got = engine.hbvedu(*args, return_storage=True, slab_steps=slab, block=64)
+            for nm, r in zip(["qsim", "snow", "soil", "s1", "s2"], ref):
+                assert_close(got[nm], r, f"variant {variant} slab={slab} {nm}")
+
+
+def test_hbvedu_negative_zero_temperature_with_a_zero_threshold():
+    """the FAST kernels read temp < T_t off the sign of temp - T_t; -0.0 - (+0.0) = -0.0 made a day with
+    temp = -0.0 (np.round(-0.04, 1)) 'cold' for T_t = 0, where the reference's -0.0 < 0.0 is False."""
+    T, N = 400, 96
+    f, P = _hbv_case(T, N, seed=4)
+    temp = f["temp"].copy()
+    temp[::3] = -0.0
+    assert np.signbit(temp[0]) and temp[0] == 0.0
+    P["T_t"][::2] = 0.0
+    P["T_t"][1::4] = -0.0
+    args = (temp, f["prec"], f["month"] - 1, f["PE_m"], f["T_m"], (5.0, 100, 3, 10), P)
+    ref = oracle.hbvedu(*args, return_storage=True)
+    for v in (1, 2, 3):
+        engine.VARIANT = v
+        try:
+            got = engine.hbvedu(*args, return_storage=True)
+        finally:
+            engine.VARIANT = 0
+        for nm, r in zip(["qsim", "snow", "soil", "s1", "s2"], ref):
+            assert_close(got[nm], r, f"variant {v} {nm}")
