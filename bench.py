@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--math", default="fast", choices=["fast", "precise"])
     ap.add_argument("--members", type=int, default=MEMBERS_PER_GPU, help="members per GPU")
     ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0, help="rrb_opts.variant (kernel A/B timing; 0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -191,6 +192,7 @@ def main():
     from rrmpg_b200 import _lib, distributed as rdist, engine
     from rrmpg_b200.models import HBVEdu
 
+    engine.VARIANT = args.variant
     rank, local_rank, world = rdist.init_process_group()
     _lib.require_gpu()
     torch.cuda.set_device(local_rank)

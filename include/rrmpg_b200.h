@@ -38,7 +38,10 @@
  *   - Every function returns RRB_OK (0) or an RRB_E* code; rrb_last_error() gives the message
  *     for the calling thread.  There is no CPU fallback: without a CUDA device the simulate
  *     calls fail with RRB_ECUDA.
- *   - Thread safety: calls are serialised per device by an internal mutex.
+ *   - Thread safety: calls are serialised per device by an internal mutex.  The per-device scratch buffers (packed
+ *     forcing etc.) are reused from call to call: every call orders its stream behind the previous device-mode call's
+ *     last kernel (one event wait), so RRB_MEM_DEVICE calls on different streams of one device run back to back,
+ *     not concurrently.
  */
 #ifndef RRMPG_B200_H
 #define RRMPG_B200_H
@@ -50,7 +53,7 @@
 extern "C" {
 #endif
 
-#define RRB_VERSION 100 /* 0.1.0 */
+#define RRB_VERSION 110 /* 0.1.1: rrb_opts grew (objective .. out_row_pitch); rrb_init_devices, rrb_state_rows */
 
 #if defined(__GNUC__)
 #define RRB_API __attribute__((visibility("default")))
@@ -76,6 +79,18 @@ enum rrb_math {
     RRB_MATH_PRECISE = 1 /* the reference's operations one for one (CUDA libm pow/tanh, IEEE division) */
 };
 
+enum rrb_objective {     /* what opts->mse receives when opts->qobs is given (rrmpg/utils/metrics.py) */
+    RRB_OBJ_MSE = 0,     /* calc_mse :110-136  mean((obs - sim)**2) */
+    RRB_OBJ_NSE = 1,     /* calc_nse :29-78    1 - sum((sim - obs)**2) / sum((obs - mean(obs))**2) */
+    RRB_OBJ_KGE = 2      /* calc_kge :139-188  1 - sqrt((r-1)**2 + (alpha-1)**2 + (beta-1)**2) */
+};
+
+enum rrb_model {         /* for rrb_state_rows */
+    RRB_MODEL_ABC = 0,
+    RRB_MODEL_HBVEDU = 1,
+    RRB_MODEL_GR4J = 2
+};
+
 #define RRB_MAX_LAYERS 16 /* Cemaneige elevation layers per call */
 #define RRB_MAX_X4 64.0   /* GR4J unit hydrograph time base per member */
 
@@ -94,12 +109,37 @@ typedef struct rrb_opts {
     const double* qobs;  /* optional [T] observed discharge: fuses the objective into the kernel */
     double* mse;         /* [N] out, required when qobs != NULL: mean((qobs - qsim[:, i])**2) */
     int64_t slab_steps;  /* RRB_MEM_HOST: timesteps per pipelined time slab, 0 = automatic */
+    /* ---- RRB_VERSION >= 110 ---- */
+    int32_t objective;   /* enum rrb_objective: the metric accumulated against qobs (registers, no [T, N] array needed) */
+    int32_t n_devices;   /* RRB_MEM_HOST, single-catchment calls: > 1 shards the members over `devices` as contiguous
+                            blocks -- one worker thread, context and stream pair per device, the forcing uploaded to each,
+                            every block's rows copied straight into its column block of the caller's [T, N] arrays.
+                            0 / 1 = opts->device only.  (member loop rrmpg/models/hbvedu.py:199-209) */
+    const int32_t* devices;   /* n_devices ordinals, NULL = 0 .. n_devices-1 */
+    const double* obs_stats;  /* HOST memory in both modes, required for NSE / KGE: (np.mean(qobs), np.std(qobs)) -- one
+                                 pair, or [C][2] for the catchment batches */
+    const double* state_in;   /* optional [rrb_state_rows(..)][N]: continue an earlier call -- the stores (and GR4J's UH1 /
+                                 UH2 buffers, which the reference neither returns nor accepts: gr4j_model.py:82-83) are
+                                 taken from here instead of the initial values, and timestep 0 of this call is an ordinary
+                                 step.  ABC, HBV-Edu, GR4J single-catchment calls; memory per opts->mem. */
+    double* state_out;        /* optional [rrb_state_rows(..)][N]: the stores after the last timestep (same layout) */
+    int64_t out_row_pitch;    /* RRB_MEM_HOST: elements between consecutive [N] rows of the caller's output arrays
+                                 (0 = N, densely packed): lets a call fill a member block of a wider [T, N_total] array */
 } rrb_opts;
 
 /* ---- library / device management ------------------------------------------------------- */
 RRB_API int rrb_version(void);
 RRB_API int rrb_device_count(void);            /* number of visible CUDA devices, 0 when none / no driver */
 RRB_API int rrb_init(int device);              /* create the per-device context eagerly (optional) */
+RRB_API int rrb_init_devices(const int32_t* devices, int n);  /* ... for a list of devices (NULL = 0 .. n-1) */
+/* rows of the state_in / state_out arrays.  Layout (one [N] row each):
+ *   ABC      S                                      (abcmodel_model.py:50)
+ *   HBV-Edu  snow, soil, s1, s2                     (hbvedu_model.py:78-81)
+ *   GR4J     S, R, uh1[0..C1), uh2[0..C2)           (gr4j_model.py:64-65, 82-83) with the unit-hydrograph capacity
+ *            class (C1, C2) of the batch: (3, 7) for x4_max <= 3, (4, 9) <= 4, (10, 21) <= 10, (64, 129) <= RRB_MAX_X4;
+ *            slots past a member's own ceil(x4) / ceil(2 x4 + 1) are 0.  A resumed call must use the same class.
+ * Returns -1 for an unknown model or x4_max > RRB_MAX_X4. */
+RRB_API int rrb_state_rows(int model, double x4_max);
 RRB_API int rrb_shutdown(void);                /* release every context, stream and scratch pool */
 RRB_API const char* rrb_last_error(void);      /* message of the last failing call on this thread */
 RRB_API int rrb_synchronize(int device);       /* wait for all library work on the device */

@@ -38,6 +38,25 @@ def build(force=False):
     return _SO
 
 
+def reference_package():
+    """The unmodified reference installed under oracle/_ref by oracle/build_ref.py (git-ignored; travels to the GPU
+    box with the snapshot).  Returns the imported `rrmpg` package, or None when it (or numba) is not available."""
+    import importlib
+    import sys
+    ref = os.path.join(_HERE, "_ref")
+    if not os.path.isdir(os.path.join(ref, "rrmpg")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        import numba  # noqa: F401
+        pkg = importlib.import_module("rrmpg")
+        importlib.import_module("rrmpg.models")
+    except Exception:
+        return None
+    return pkg if os.path.abspath(pkg.__file__).startswith(ref) else None
+
+
 def lib():
     global _lib
     if _lib is None:

@@ -15,6 +15,8 @@ LIB_PATH = os.environ.get("RRMPG_B200_LIB", os.path.join(_HERE, "librrmpg_b200.s
 RRB_OK, RRB_EINVAL, RRB_ECUDA, RRB_EUNSUPPORTED, RRB_ENOMEM = range(5)
 MEM_HOST, MEM_DEVICE = 0, 1
 MATH_FAST, MATH_PRECISE = 0, 1
+OBJ_MSE, OBJ_NSE, OBJ_KGE = 0, 1, 2
+MODEL_ABC, MODEL_HBVEDU, MODEL_GR4J = 0, 1, 2
 MAX_LAYERS = 16
 MAX_X4 = 64.0
 
@@ -27,13 +29,18 @@ class Opts(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("mem", C.c_int32),
                 ("math", C.c_int32), ("stream", C.c_void_p), ("block", C.c_int32),
                 ("variant", C.c_int32), ("x4_max", C.c_double), ("qobs", C.c_void_p),
-                ("mse", C.c_void_p), ("slab_steps", C.c_int64)]
+                ("mse", C.c_void_p), ("slab_steps", C.c_int64),
+                ("objective", C.c_int32), ("n_devices", C.c_int32), ("devices", C.c_void_p),
+                ("obs_stats", C.c_void_p), ("state_in", C.c_void_p), ("state_out", C.c_void_p),
+                ("out_row_pitch", C.c_int64)]
 
 
 _SIGS = {
     "rrb_version": (C.c_int, []),
     "rrb_device_count": (C.c_int, []),
     "rrb_init": (C.c_int, [C.c_int]),
+    "rrb_init_devices": (C.c_int, [C.c_void_p, C.c_int]),
+    "rrb_state_rows": (C.c_int, [C.c_int, C.c_double]),
     "rrb_shutdown": (C.c_int, []),
     "rrb_last_error": (C.c_char_p, []),
     "rrb_synchronize": (C.c_int, [C.c_int]),

@@ -6,6 +6,7 @@
 // return_storage), ~5 fp64 instructions.
 #include "rr_common.cuh"
 #include "rr_kernels.h"
+#include "rr_objective.cuh"
 
 namespace rrb {
 
@@ -32,18 +33,20 @@ __global__ void abc_kernel(const double* __restrict__ F, double s0, const double
     const double omab = 1 - a - b;  // loop invariants of abcmodel_model.py:56,59
     const double omc = 1 - c;
     double S = s0;
-    double acc = 0.0;
-    if (slab.t_begin > 0) {
+    ObjAcc acc;
+    acc.reset();
+    if (slab_loads_state(slab)) {
         S = slab.state[i];
-        if (OBJ) acc = slab.state[N + i];
+        if (OBJ && slab.t_begin > 0) acc.load(slab.state, 1, N, i, obj);
     }
+    const bool skip_t0 = !slab.resume;
     double* q = qsim ? qsim + i - slab.row0 * N : nullptr;
     double* st = STORAGE ? storage + i - slab.row0 * N : nullptr;
 
     stream_forcing<kAbcR, kAbcTT>(F, slab.t_begin, slab.t_end, [&](int64_t t, const double* f) {
         const double p = f[0];
         double qv;
-        if (t == 0) {
+        if (t == 0 && skip_t0) {
             qv = 0.0;  // abcmodel_model.py:53 -- the loop starts at t = 1, qsim[0] stays 0
         } else {
             qv = omab * p + c * S;  // :56
@@ -53,18 +56,15 @@ __global__ void abc_kernel(const double* __restrict__ F, double s0, const double
             if (q) st_stream(q + t * N, qv);
             if (STORAGE) st_stream(st + t * N, S);
         }
-        if (OBJ) {
-            const double d = obj.qobs[t] - qv;
-            acc += d * d;
-        }
+        if (OBJ) acc.add(obj.qobs[t], qv, obj);
     });
 
     if (active) {
         if (slab.save_state) {
             slab.state[i] = S;
-            if (OBJ) slab.state[N + i] = acc;
+            if (OBJ && slab.save_state == 1) acc.save(slab.state, 1, N, i, obj);
         }
-        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i] = acc / (double)obj.T;
+        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i] = acc.finish(obj);
     }
 }
 
@@ -87,12 +87,12 @@ __global__ void abc_pair_kernel(const double* __restrict__ F, double s0, const d
     const double omab1 = 1 - a1 - b1, omc1 = 1 - c1;
     double S0 = s0, S1 = s0;
     int64_t t_first = slab.t_begin;
-    if (slab.t_begin > 0) {
+    if (slab_loads_state(slab)) {
         S0 = slab.state[i];
         S1 = slab.state[i + 1];
     }
     double* q = qsim + i + (slab.t_begin - slab.row0) * N;
-    if (slab.t_begin == 0 && slab.t_end > 0) {  // abcmodel_model.py:53 -- the loop starts at t = 1, qsim[0] stays 0
+    if (slab.t_begin == 0 && slab.t_end > 0 && !slab.resume) {  // abcmodel_model.py:53 -- the loop starts at t = 1, qsim[0] stays 0
         st_stream_v2(q, 0.0, 0.0);
         q += N;
         t_first = 1;
@@ -112,7 +112,7 @@ __global__ void abc_pair_kernel(const double* __restrict__ F, double s0, const d
     }
 }
 
-int state_slots_abc() { return 2; }
+int state_slots_abc() { return 1 + kObjSlots; }
 
 cudaError_t launch_abc(const double* F, int64_t T, double s0, const double* params, int64_t N, double* qsim,
                        double* storage, const Slab& slab, const Objective& obj, const LaunchCfg& cfg) {

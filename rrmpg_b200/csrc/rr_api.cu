@@ -14,6 +14,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rrmpg_b200.h"
@@ -24,6 +25,8 @@ namespace rrb {
 
 static_assert((int)RRB_MATH_FAST == (int)RRB_MATH_FAST_ && (int)RRB_MATH_PRECISE == (int)RRB_MATH_PRECISE_, "math enum mismatch");
 static_assert(RRB_MAX_LAYERS == kCemaMaxLayers, "layer cap mismatch");
+static_assert((int)RRB_OBJ_MSE == (int)RRB_OBJ_MSE_ && (int)RRB_OBJ_NSE == (int)RRB_OBJ_NSE_ && (int)RRB_OBJ_KGE == (int)RRB_OBJ_KGE_,
+              "objective enum mismatch");
 
 static thread_local std::string g_err;
 
@@ -101,6 +104,7 @@ enum BufSlot {
     B_QOBS,
     B_MSE,
     B_SCALAR,
+    B_OBS,     // catchment batches: (mean, std) of every qobs series
     B_OUT0,    // output ring: B_OUT0 + 2*k + slot, k < 8
     B_COUNT = B_OUT0 + 16
 };
@@ -110,6 +114,8 @@ struct Ctx {
     int sm_count = 148;
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_scratch = nullptr;  // behind the last kernel of the latest device-mode call (see HostDrain)
+    bool scratch_busy = false;
     std::mutex mu;
     void* buf[B_COUNT] = {};
     size_t cap[B_COUNT] = {};
@@ -151,6 +157,9 @@ struct Ctx {
             if (ev_free[i]) cudaEventDestroy(ev_free[i]);
             ev_done[i] = ev_free[i] = nullptr;
         }
+        if (ev_scratch) cudaEventDestroy(ev_scratch);
+        ev_scratch = nullptr;
+        scratch_busy = false;
         if (compute) cudaStreamDestroy(compute);
         if (copy) cudaStreamDestroy(copy);
         compute = copy = nullptr;
@@ -183,6 +192,7 @@ static int get_ctx(int device, Ctx** out) {
             RRB_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
             RRB_CUDA(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
         }
+        RRB_CUDA(cudaEventCreateWithFlags(&c->ev_scratch, cudaEventDisableTiming));
         it = g_ctx.emplace(device, std::move(c)).first;
     }
     *out = it->second.get();
@@ -196,6 +206,13 @@ struct Opts {
     const double* qobs = nullptr;
     double* mse = nullptr;
     int64_t slab_steps = 0;
+    int objective = RRB_OBJ_MSE;
+    int n_devices = 0;
+    const int32_t* devices = nullptr;
+    const double* obs_stats = nullptr;  // host [C][2]
+    const double* state_in = nullptr;
+    double* state_out = nullptr;
+    int64_t out_row_pitch = 0;
 };
 
 static int parse_opts(const rrb_opts* o, Opts* out) {
@@ -218,6 +235,22 @@ static int parse_opts(const rrb_opts* o, Opts* out) {
     out->qobs = o->qobs;
     out->mse = o->mse;
     out->slab_steps = o->slab_steps;
+    if (o->objective != RRB_OBJ_MSE && o->objective != RRB_OBJ_NSE && o->objective != RRB_OBJ_KGE)
+        return fail(RRB_EINVAL, "rrb_opts.objective = %d", o->objective);
+    if (o->qobs && o->objective != RRB_OBJ_MSE && !o->obs_stats)
+        return fail(RRB_EINVAL, "rrb_opts.obs_stats (mean and standard deviation of qobs) is required for NSE / KGE");
+    if (o->n_devices < 0) return fail(RRB_EINVAL, "rrb_opts.n_devices = %d", o->n_devices);
+    if (o->n_devices > 1 && o->mem != RRB_MEM_HOST)
+        return fail(RRB_EINVAL, "rrb_opts.n_devices > 1 needs RRB_MEM_HOST (device buffers live on one device)");
+    if (o->out_row_pitch < 0) return fail(RRB_EINVAL, "rrb_opts.out_row_pitch < 0");
+    if (o->out_row_pitch > 0 && o->mem != RRB_MEM_HOST) return fail(RRB_EINVAL, "rrb_opts.out_row_pitch needs RRB_MEM_HOST");
+    out->objective = o->objective;
+    out->n_devices = o->n_devices;
+    out->devices = o->devices;
+    out->obs_stats = o->obs_stats;
+    out->state_in = o->state_in;
+    out->state_out = o->state_out;
+    out->out_row_pitch = o->out_row_pitch;
     return RRB_OK;
 }
 
@@ -233,7 +266,8 @@ struct OutArr {
 struct Job {
     int64_t T = 0, N = 0;
     std::vector<OutArr> outs;
-    int state_slots = 0;
+    int state_slots = 0;   // rows of the carry buffer: the model's own + kObjSlots objective rows
+    bool resumable = false;  // the entry point supports rrb_opts.state_in / state_out
     // launch(slab, out_ptrs (device, row0-relative), objective, cfg)
     std::function<cudaError_t(const Slab&, double* const*, const Objective&, const LaunchCfg&)> launch;
 };
@@ -247,8 +281,19 @@ static size_t multi_chunk_bytes() {
     return v > 0 ? v : kSlabTargetBytes * 2;
 }
 
+static Objective make_objective(const Opts& o, const double* d_qobs, double* d_mse, int64_t T, int64_t catchment = 0) {
+    Objective obj{d_qobs, d_mse, T, o.objective, 0.0, 1.0, nullptr};
+    if (o.obs_stats) {
+        obj.obs_mean = o.obs_stats[2 * catchment];
+        obj.obs_std = o.obs_stats[2 * catchment + 1];
+    }
+    return obj;
+}
+
 // Runs job.launch over [0, T).  Device mode: one launch straight into the caller's arrays.
 // Host mode: time slabs through a two-deep device ring; the D2H of slab k overlaps slab k+1.
+// rrb_opts.state_in / state_out (resume): the model rows of the carry buffer are read before the first and handed
+// out after the last slab; with state_in timestep 0 is an ordinary step of a continued series (Slab::resume).
 static int run_job(Ctx& c, const Opts& o, const Job& job, const double* d_qobs, double* d_mse) {
     const int64_t T = job.T, N = job.N;
     const int nout = (int)job.outs.size();
@@ -257,18 +302,33 @@ static int run_job(Ctx& c, const Opts& o, const Job& job, const double* d_qobs, 
     cfg.math = o.math;
     cfg.sm_count = c.sm_count;
     cfg.variant = o.variant;
-    Objective obj{d_qobs, d_mse, T};
+    Objective obj = make_objective(o, d_qobs, d_mse, T);
+    const bool resume = o.state_in != nullptr, want_state = o.state_out != nullptr;
+    if ((resume || want_state) && !job.resumable)
+        return fail(RRB_EUNSUPPORTED, "state_in / state_out are supported by the ABC, HBV-Edu and GR4J entry points only");
+    const int model_rows = job.state_slots - kObjSlots;
+    const size_t model_state_bytes = sizeof(double) * (size_t)model_rows * (size_t)N;
 
     if (o.mem == RRB_MEM_DEVICE) {
         cfg.stream = o.stream;
         std::vector<double*> ptrs(nout);
         for (int k = 0; k < nout; ++k) ptrs[k] = job.outs[k].user;
-        Slab slab{0, T, 0, nullptr, 0};
+        double* state = nullptr;
+        if (want_state) {
+            state = o.state_out;
+            if (resume && o.state_in != o.state_out)
+                RRB_CUDA(cudaMemcpyAsync(o.state_out, o.state_in, model_state_bytes, cudaMemcpyDeviceToDevice, o.stream));
+        } else if (resume) {
+            state = const_cast<double*>(o.state_in);  // read only: save_state = 0
+        }
+        Slab slab{0, T, 0, state, want_state ? 2 : 0, resume ? 1 : 0};
         RRB_CUDA(job.launch(slab, ptrs.data(), obj, cfg));
         return RRB_OK;
     }
 
     cfg.stream = c.compute;
+    const int64_t pitch = o.out_row_pitch > 0 ? o.out_row_pitch : N;  // elements between rows of the caller's arrays
+    if (pitch < N) return fail(RRB_EINVAL, "rrb_opts.out_row_pitch = %lld < N = %lld", (long long)pitch, (long long)N);
     int64_t bytes_per_step = 0;
     for (auto& a : job.outs)
         if (a.user) bytes_per_step += a.row_elems * (int64_t)sizeof(double);
@@ -284,11 +344,12 @@ static int run_job(Ctx& c, const Opts& o, const Job& job, const double* d_qobs, 
     const bool ring = nslabs > 1;
 
     double* state = nullptr;
-    if (ring) {
+    if (ring || resume || want_state) {
         void* p = nullptr;
         int rc = c.ensure(B_STATE, sizeof(double) * (size_t)job.state_slots * (size_t)N, &p);
         if (rc) return rc;
         state = (double*)p;
+        if (resume) RRB_CUDA(cudaMemcpyAsync(state, o.state_in, model_state_bytes, cudaMemcpyHostToDevice, c.compute));
     }
     std::vector<double*> dev[2];
     for (int s = 0; s < (ring ? 2 : 1); ++s) {
@@ -305,21 +366,36 @@ static int run_job(Ctx& c, const Opts& o, const Job& job, const double* d_qobs, 
         const int s = k & 1;
         const int64_t t0 = (int64_t)k * steps, t1 = std::min(T, t0 + steps);
         if (k >= 2) RRB_CUDA(cudaStreamWaitEvent(c.compute, c.ev_free[s], 0));
-        Slab slab{t0, t1, t0, state, ring ? 1 : 0};
+        const bool last = k == nslabs - 1;
+        Slab slab{t0, t1, t0, state, (ring && !last) || (last && want_state) ? 1 : 0, (resume && k == 0) ? 1 : 0};
         RRB_CUDA(job.launch(slab, dev[s].data(), obj, cfg));
         RRB_CUDA(cudaEventRecord(c.ev_done[s], c.compute));
         RRB_CUDA(cudaStreamWaitEvent(c.copy, c.ev_done[s], 0));
         for (int j = 0; j < nout; ++j) {
             if (!job.outs[j].user) continue;
             const size_t row = (size_t)job.outs[j].row_elems;
-            RRB_CUDA(cudaMemcpyAsync(job.outs[j].user + (size_t)t0 * row, dev[s][j],
-                                     sizeof(double) * (size_t)(t1 - t0) * row, cudaMemcpyDeviceToHost, c.copy));
+            if (pitch == N) {
+                RRB_CUDA(cudaMemcpyAsync(job.outs[j].user + (size_t)t0 * row, dev[s][j],
+                                         sizeof(double) * (size_t)(t1 - t0) * row, cudaMemcpyDeviceToHost, c.copy));
+            } else {
+                // the caller's rows are `pitch` elements apart (a member block of a wider [T, N_total] array): every
+                // [N] row -- [T, L, N] storages hold L of them per timestep -- lands at its own pitch
+                const size_t rows_per_step = row / (size_t)N;
+                RRB_CUDA(cudaMemcpy2DAsync(job.outs[j].user + (size_t)t0 * rows_per_step * (size_t)pitch,
+                                           sizeof(double) * (size_t)pitch, dev[s][j], sizeof(double) * (size_t)N,
+                                           sizeof(double) * (size_t)N, (size_t)(t1 - t0) * rows_per_step,
+                                           cudaMemcpyDeviceToHost, c.copy));
+            }
         }
         RRB_CUDA(cudaEventRecord(c.ev_free[s], c.copy));
     }
     if (o.qobs) {
         RRB_CUDA(cudaStreamWaitEvent(c.copy, c.ev_done[(nslabs - 1) & 1], 0));
         RRB_CUDA(cudaMemcpyAsync(o.mse, d_mse, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, c.copy));
+    }
+    if (want_state) {
+        RRB_CUDA(cudaStreamWaitEvent(c.copy, c.ev_done[(nslabs - 1) & 1], 0));
+        RRB_CUDA(cudaMemcpyAsync(o.state_out, state, model_state_bytes, cudaMemcpyDeviceToHost, c.copy));
     }
     RRB_CUDA(cudaStreamSynchronize(c.copy));
     RRB_CUDA(cudaStreamSynchronize(c.compute));
@@ -348,17 +424,31 @@ struct Prepared {
     const double* d_params = nullptr;
     const double* d_qobs = nullptr;
     double* d_mse = nullptr;
+    const double* d_obs_stats = nullptr;  // catchment batches: device copy of rrb_opts.obs_stats [C][2]
 };
 
-// Host mode hands the caller's buffers to asynchronous copies.  Whatever path leaves an entry point (an error return
-// in the middle of the prologue or of the slab ring included), nothing may still be reading or writing caller memory:
-// the guard drains both context streams on scope exit (a no-op after a successful run_job, which has synchronised).
+// Guard of one entry point, taken right after the context mutex.
+//  * Host mode hands the caller's buffers to asynchronous copies.  Whatever path leaves an entry point (an error return
+//    in the middle of the prologue or of the slab ring included), nothing may still be reading or writing caller memory:
+//    the guard drains both context streams on scope exit (a no-op after a successful run_job, which has synchronised).
+//  * The per-context scratch buffers (packed forcing, G_tresh, scalar inits, flags) are written and read asynchronously
+//    on the stream of the call.  A device-mode call returns while its kernels may still be reading them, and the next
+//    call -- on another user stream, or a host-mode call on the context's own stream -- would re-pack into the same
+//    buffers.  Every call therefore first makes its stream wait for the event the previous device-mode call recorded
+//    behind its last kernel, and a device-mode call records that event on exit.
 struct HostDrain {
     const Prepared& P;
+    explicit HostDrain(const Prepared& p) : P(p) {
+        if (P.c && P.c->scratch_busy) (void)cudaStreamWaitEvent(P.s, P.c->ev_scratch, 0);
+    }
     ~HostDrain() {
-        if (P.c && P.o.mem == RRB_MEM_HOST) {
+        if (!P.c) return;
+        if (P.o.mem == RRB_MEM_HOST) {
             (void)cudaStreamSynchronize(P.c->compute);
             (void)cudaStreamSynchronize(P.c->copy);
+            P.c->scratch_busy = false;  // the wait above and this drain: every earlier user has finished
+        } else {
+            P.c->scratch_busy = cudaEventRecord(P.c->ev_scratch, P.s) == cudaSuccess;
         }
     }
 };
@@ -448,7 +538,8 @@ static int run_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const std::ve
     std::vector<double*> ptrs(no);
     if (!host) {
         for (int j = 0; j < no; ++j) ptrs[j] = outs[j].ptr;
-        Objective obj{P.d_qobs, P.d_mse, T};
+        Objective obj = make_objective(P.o, P.d_qobs, P.d_mse, T);
+        obj.obs_stats = P.d_obs_stats;
         RRB_CUDA(launch(0, C, ptrs.data(), obj, cfg));
         return RRB_OK;
     }
@@ -472,7 +563,8 @@ static int run_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const std::ve
         const int sidx = k & 1;
         const int64_t c0 = (int64_t)k * cc, c1 = std::min(C, c0 + cc);
         if (k >= 2) RRB_CUDA(cudaStreamWaitEvent(c.compute, c.ev_free[sidx], 0));
-        Objective obj{P.d_qobs ? P.d_qobs + c0 * T : nullptr, P.d_mse ? P.d_mse + c0 * N : nullptr, T};
+        Objective obj = make_objective(P.o, P.d_qobs ? P.d_qobs + c0 * T : nullptr, P.d_mse ? P.d_mse + c0 * N : nullptr, T, c0);
+        obj.obs_stats = P.d_obs_stats ? P.d_obs_stats + 2 * c0 : nullptr;
         RRB_CUDA(launch(c0, c1, dev[sidx].data(), obj, cfg));
         RRB_CUDA(cudaEventRecord(c.ev_done[sidx], c.compute));
         RRB_CUDA(cudaStreamWaitEvent(c.copy, c.ev_done[sidx], 0));
@@ -489,6 +581,17 @@ static int run_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const std::ve
     }
     RRB_CUDA(cudaStreamSynchronize(c.copy));
     RRB_CUDA(cudaStreamSynchronize(c.compute));
+    return RRB_OK;
+}
+
+// per-catchment (mean, std) of the observations (host memory in both modes) -> device array read by the kernels
+static int stage_obs_stats(Prepared& P, int64_t C) {
+    if (!P.o.obs_stats) return RRB_OK;
+    void* p = nullptr;
+    int rc = P.c->ensure(B_OBS, sizeof(double) * 2 * (size_t)C, &p);
+    if (rc) return rc;
+    RRB_CUDA(cudaMemcpyAsync(p, P.o.obs_stats, sizeof(double) * 2 * (size_t)C, cudaMemcpyHostToDevice, P.s));
+    P.d_obs_stats = (const double*)p;
     return RRB_OK;
 }
 
@@ -510,10 +613,72 @@ static int stage_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const doubl
         } else {
             P.d_mse = P.o.mse;
         }
+        if ((rc = stage_obs_stats(P, C))) return rc;
     }
     return RRB_OK;
 }
 
+
+
+// ----------------------------------------------------------------------------------------
+// In-library multi-GPU (SURVEY.md section 8b "Threading" / 8e "Process model"): a host-mode single-catchment call
+// with rrb_opts.n_devices > 1 splits the ensemble [0, N) into contiguous member blocks, one per device, and runs the
+// same entry point for every block on its own worker thread (own context, streams and scratch per device).  The
+// member-independent forcing is uploaded to every device (<= 0.5 MB); every block's rows are copied straight into its
+// column block of the caller's [T, N] / [T, L, N] arrays (rrb_opts.out_row_pitch = N).  No collective: members are
+// independent given the forcing (the loop being sharded is rrmpg/models/hbvedu.py:199-209 and siblings).
+// ----------------------------------------------------------------------------------------
+static bool wants_sharding(const rrb_opts* o, int64_t N) {
+    return o && o->struct_size == (int32_t)sizeof(rrb_opts) && o->n_devices > 1 && o->mem == RRB_MEM_HOST && N > 0;
+}
+template <class T_>
+static T_* shifted(T_* p, int64_t elems) { return p ? p + elems : nullptr; }
+
+// call(sub_opts, lo, n): the entry point for members [lo, lo + n)
+template <class Call>
+static int shard_members(const rrb_opts* opts, int64_t N, Call&& call) {
+    if (opts->state_in || opts->state_out)
+        return fail(RRB_EUNSUPPORTED, "state_in / state_out are not supported together with n_devices > 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(RRB_ECUDA, "no CUDA device available; rrmpg_b200 has no CPU fallback");
+    }
+    std::vector<int> devs;
+    for (int k = 0; k < opts->n_devices; ++k) {
+        const int d = opts->devices ? opts->devices[k] : k;
+        if (d < 0 || d >= ndev) return fail(RRB_EINVAL, "rrb_opts.devices[%d] = %d out of range (%d visible)", k, d, ndev);
+        devs.push_back(d);  // (a device listed twice gets two blocks, serialised by its context mutex: legal, used by tests)
+    }
+    // contiguous blocks, multiples of 64 members (16-byte aligned rows, whole warps) except the last
+    const int64_t D = (int64_t)devs.size();
+    int64_t per = (N + D - 1) / D;
+    per = (per + 63) & ~int64_t(63);
+    struct Part { int64_t lo, n; int rc; std::string err; };
+    std::vector<Part> parts;
+    for (int64_t lo = 0; lo < N; lo += per) parts.push_back(Part{lo, std::min(per, N - lo), RRB_OK, ""});
+    const int64_t pitch = opts->out_row_pitch > 0 ? opts->out_row_pitch : N;
+    std::vector<std::thread> workers;
+    for (size_t k = 0; k < parts.size(); ++k) {
+        workers.emplace_back([&, k]() {
+            rrb_opts so = *opts;
+            so.n_devices = 0;
+            so.devices = nullptr;
+            so.device = devs[k];
+            so.out_row_pitch = pitch;
+            so.mse = shifted(opts->mse, parts[k].lo);
+            parts[k].rc = call(&so, parts[k].lo, parts[k].n);
+            if (parts[k].rc != RRB_OK) parts[k].err = g_err;  // thread-local: carry the message over
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (auto& pt : parts)
+        if (pt.rc != RRB_OK) {
+            g_err = pt.err;
+            return pt.rc;
+        }
+    return RRB_OK;
+}
 
 // ----------------------------------------------------------------------------------------
 // C ABI
@@ -534,6 +699,25 @@ int rrb_device_count(void) {
 int rrb_init(int device) {
     Ctx* c;
     return get_ctx(device, &c);
+}
+
+int rrb_init_devices(const int32_t* devices, int n) {
+    if (n < 1) return fail(RRB_EINVAL, "rrb_init_devices: n = %d", n);
+    for (int k = 0; k < n; ++k) {
+        Ctx* c;
+        int rc = get_ctx(devices ? devices[k] : k, &c);
+        if (rc) return rc;
+    }
+    return RRB_OK;
+}
+
+int rrb_state_rows(int model, double x4_max) {
+    switch (model) {
+        case RRB_MODEL_ABC: return state_slots_abc() - kObjSlots;
+        case RRB_MODEL_HBVEDU: return state_slots_hbvedu() - kObjSlots;
+        case RRB_MODEL_GR4J: return (x4_max <= RRB_MAX_X4) ? state_slots_gr4j(x4_max) - kObjSlots : -1;
+        default: return -1;
+    }
 }
 
 int rrb_shutdown(void) {
@@ -610,6 +794,10 @@ void rrb_host_pool_trim(void) {
 // ---- ABC ----
 int rrb_abc_simulate(const double* prec, int64_t T, double initial_state, const double* params, int64_t N,
                      double* qsim, double* storage, const rrb_opts* opts) {
+    if (wants_sharding(opts, N))
+        return shard_members(opts, N, [&](const rrb_opts* so, int64_t lo, int64_t n) {
+            return rrb_abc_simulate(prec, T, initial_state, params + lo * 3, n, shifted(qsim, lo), shifted(storage, lo), so);
+        });
     Prepared P;
     int rc = prepare(opts, T, N, params, 3, &P);
     if (rc) return rc;
@@ -617,7 +805,7 @@ int rrb_abc_simulate(const double* prec, int64_t T, double initial_state, const 
     if (!qsim && !P.o.qobs) return fail(RRB_EINVAL, "nothing to compute: qsim is NULL and no objective requested");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
-    HostDrain drain{P};
+    HostDrain drain(P);
     const double* d_prec;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)T, &d_prec))) return rc;
     if ((rc = stage_common(&P, T, N, params, 3))) return rc;
@@ -628,6 +816,7 @@ int rrb_abc_simulate(const double* prec, int64_t T, double initial_state, const 
     job.T = T; job.N = N;
     job.outs = {{qsim, N}, {storage, N}};
     job.state_slots = state_slots_abc();
+    job.resumable = true;
     const double* dp = P.d_params;
     job.launch = [=](const Slab& sl, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
         return launch_abc((const double*)F, T, initial_state, dp, N, out[0], out[1], sl, ob, cfg);
@@ -639,6 +828,11 @@ int rrb_abc_simulate(const double* prec, int64_t T, double initial_state, const 
 int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
                         const double* T_m, int64_t T, const double* inits, const double* params, int64_t N,
                         double* qsim, double* snow, double* soil, double* s1, double* s2, const rrb_opts* opts) {
+    if (wants_sharding(opts, N))
+        return shard_members(opts, N, [&](const rrb_opts* so, int64_t lo, int64_t n) {
+            return rrb_hbvedu_simulate(temp, prec, month0, PE_m, T_m, T, inits, params + lo * 11, n, shifted(qsim, lo),
+                                       shifted(snow, lo), shifted(soil, lo), shifted(s1, lo), shifted(s2, lo), so);
+        });
     Prepared P;
     int rc = prepare(opts, T, N, params, 11, &P);
     if (rc) return rc;
@@ -648,7 +842,7 @@ int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* mo
     if (!qsim && !P.o.qobs && nst == 0) return fail(RRB_EINVAL, "nothing to compute");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
-    HostDrain drain{P};
+    HostDrain drain(P);
     const double *d_temp, *d_prec, *d_pe, *d_tm;
     const int8_t* d_month;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, temp, (size_t)T, &d_temp))) return rc;
@@ -666,6 +860,7 @@ int rrb_hbvedu_simulate(const double* temp, const double* prec, const int8_t* mo
     job.T = T; job.N = N;
     job.outs = {{qsim, N}, {snow, N}, {soil, N}, {s1, N}, {s2, N}};
     job.state_slots = state_slots_hbvedu();
+    job.resumable = true;
     const double* dp = P.d_params;
     const double i0 = in4[0], i1 = in4[1], i2 = in4[2], i3 = in4[3];
     job.launch = [=](const Slab& sl, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
@@ -692,7 +887,7 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
     if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
     if (N == 0 || C == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
-    HostDrain drain{P};
+    HostDrain drain(P);
     Ctx& c = *P.c;
     const bool host = P.o.mem == RRB_MEM_HOST;
     const double *d_temp, *d_prec, *d_pe, *d_tm;
@@ -716,6 +911,7 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
         } else {
             P.d_mse = P.o.mse;
         }
+        if ((rc = stage_obs_stats(P, C))) return rc;
     }
     const int64_t Tpad = padded_steps(T, kHbvTT);
     void* F = nullptr;
@@ -734,8 +930,9 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
 
     if (!host) {
         Batch b{(int)C, Tpad * kHbvR, T * N, (const double*)d_inits};
-        Slab slab{0, T, 0, nullptr, 0};
-        Objective obj{P.d_qobs, P.d_mse, T};
+        Slab slab{0, T, 0, nullptr, 0, 0};
+        Objective obj = make_objective(P.o, P.d_qobs, P.d_mse, T);
+        obj.obs_stats = P.d_obs_stats;
         RRB_CUDA(launch_hbvedu((const double*)F, T, zero4, P.d_params, N, qsim, snow, soil, s1, s2, slab, obj, cfg,
                                hbv_flag, b));
         return RRB_OK;
@@ -761,8 +958,9 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
         const int64_t c0 = (int64_t)k * cc, c1 = std::min(C, c0 + cc);
         if (k >= 2) RRB_CUDA(cudaStreamWaitEvent(c.compute, c.ev_free[sidx], 0));
         Batch b{(int)(c1 - c0), Tpad * kHbvR, T * N, (const double*)d_inits + 4 * c0};
-        Slab slab{0, T, 0, nullptr, 0};
-        Objective obj{P.d_qobs ? P.d_qobs + c0 * T : nullptr, P.d_mse ? P.d_mse + c0 * N : nullptr, T};
+        Slab slab{0, T, 0, nullptr, 0, 0};
+        Objective obj = make_objective(P.o, P.d_qobs ? P.d_qobs + c0 * T : nullptr, P.d_mse ? P.d_mse + c0 * N : nullptr, T, c0);
+        obj.obs_stats = P.d_obs_stats ? P.d_obs_stats + 2 * c0 : nullptr;
         RRB_CUDA(launch_hbvedu((const double*)F + c0 * Tpad * kHbvR, T, zero4, P.d_params + c0 * N * 11, N, dev[sidx][0],
                                dev[sidx][1], dev[sidx][2], dev[sidx][3], dev[sidx][4], slab, obj, cfg, hbv_flag, b));
         RRB_CUDA(cudaEventRecord(c.ev_done[sidx], c.compute));
@@ -786,6 +984,11 @@ int rrb_hbvedu_simulate_multi(const double* temp, const double* prec, const int8
 int rrb_gr4j_simulate(const double* prec, const double* etp, int64_t T, double s_init, double r_init,
                       const double* params, int64_t N, double* qsim, double* s_store, double* r_store,
                       const rrb_opts* opts) {
+    if (wants_sharding(opts, N))
+        return shard_members(opts, N, [&](const rrb_opts* so, int64_t lo, int64_t n) {
+            return rrb_gr4j_simulate(prec, etp, T, s_init, r_init, params + lo * 4, n, shifted(qsim, lo),
+                                     shifted(s_store, lo), shifted(r_store, lo), so);
+        });
     Prepared P;
     int rc = prepare(opts, T, N, params, 4, &P);
     if (rc) return rc;
@@ -794,7 +997,7 @@ int rrb_gr4j_simulate(const double* prec, const double* etp, int64_t T, double s
     if (!qsim && !P.o.qobs && !s_store) return fail(RRB_EINVAL, "nothing to compute");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
-    HostDrain drain{P};
+    HostDrain drain(P);
     const double *d_prec, *d_etp;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)T, &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, etp, (size_t)T, &d_etp))) return rc;
@@ -811,6 +1014,7 @@ int rrb_gr4j_simulate(const double* prec, const double* etp, int64_t T, double s
     job.T = T; job.N = N;
     job.outs = {{qsim, N}, {s_store, N}, {r_store, N}};
     job.state_slots = state_slots_gr4j(x4_max);
+    job.resumable = true;
     const double* dp = P.d_params;
     job.launch = [=](const Slab& sl, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
         return launch_gr4j((const double*)F, T, s_init, r_init, dp, N, x4_max, out[0], out[1], out[2], sl, ob, cfg);
@@ -823,6 +1027,12 @@ int rrb_cemaneige_simulate(const double* prec, const double* mean_temp, const do
                            int64_t L, double snow_pack_init, double thermal_state_init, const double* params,
                            int64_t param_stride, int64_t N, double* outflow, double* G, double* eTG,
                            const rrb_opts* opts) {
+    if (wants_sharding(opts, N))  // [T, L, N] storages: every [N] row of a member block starts lo elements into the row
+        return shard_members(opts, N, [&](const rrb_opts* so, int64_t lo, int64_t n) {
+            return rrb_cemaneige_simulate(prec, mean_temp, frac_solid, T, L, snow_pack_init, thermal_state_init,
+                                          params + lo * param_stride, param_stride, n, shifted(outflow, lo), shifted(G, lo),
+                                          shifted(eTG, lo), so);
+        });
     Prepared P;
     int rc = prepare(opts, T, N, params, param_stride, &P);
     if (rc) return rc;
@@ -834,7 +1044,7 @@ int rrb_cemaneige_simulate(const double* prec, const double* mean_temp, const do
     if (!outflow && !P.o.qobs && !G) return fail(RRB_EINVAL, "nothing to compute");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
-    HostDrain drain{P};
+    HostDrain drain(P);
     const double *d_prec, *d_mt, *d_fr;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(T * L), &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(T * L), &d_mt))) return rc;
@@ -862,6 +1072,12 @@ int rrb_cemaneigegr4j_simulate(const double* prec, const double* mean_temp, cons
                                const double* frac_solid, int64_t T, int64_t L, const double* inits,
                                const double* params, int64_t N, double* qsim, double* G, double* eTG,
                                double* s_store, double* r_store, const rrb_opts* opts) {
+    if (wants_sharding(opts, N))
+        return shard_members(opts, N, [&](const rrb_opts* so, int64_t lo, int64_t n) {
+            return rrb_cemaneigegr4j_simulate(prec, mean_temp, etp, frac_solid, T, L, inits, params + lo * 6, n,
+                                              shifted(qsim, lo), shifted(G, lo), shifted(eTG, lo), shifted(s_store, lo),
+                                              shifted(r_store, lo), so);
+        });
     Prepared P;
     int rc = prepare(opts, T, N, params, 6, &P);
     if (rc) return rc;
@@ -873,7 +1089,7 @@ int rrb_cemaneigegr4j_simulate(const double* prec, const double* mean_temp, cons
     if (!qsim && !P.o.qobs && nst == 0) return fail(RRB_EINVAL, "nothing to compute");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
-    HostDrain drain{P};
+    HostDrain drain(P);
     const double *d_prec, *d_mt, *d_fr, *d_etp;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(T * L), &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(T * L), &d_mt))) return rc;
@@ -913,6 +1129,13 @@ static int snowice_simulate(int family, const double* prec, const double* mean_t
                             int n_storage_expected, const rrb_opts* opts) {
     const bool hyst = family & 1, ice = family & 2;
     const int k = 6 + (hyst ? 2 : 0) + (ice ? 1 : 0);
+    if (wants_sharding(opts, N))
+        return shard_members(opts, N, [&](const rrb_opts* so, int64_t lo, int64_t n) {
+            SnowIceOut so_out{shifted(o.qsim, lo), shifted(o.G, lo), shifted(o.eTG, lo), shifted(o.s_store, lo),
+                              shifted(o.r_store, lo), shifted(o.sca, lo), shifted(o.icemelt, lo), shifted(o.snowmelt, lo)};
+            return snowice_simulate(family, prec, mean_temp, etp, frac_ice, frac_solid, T, L, inits, params + lo * k, n,
+                                    so_out, n_storage_given, n_storage_expected, so);
+        });
     Prepared P;
     int rc = prepare(opts, T, N, params, k, &P);
     if (rc) return rc;
@@ -925,7 +1148,7 @@ static int snowice_simulate(int family, const double* prec, const double* mean_t
     if (!o.qsim && !P.o.qobs && n_storage_given == 0) return fail(RRB_EINVAL, "nothing to compute");
     if (N == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
-    HostDrain drain{P};
+    HostDrain drain(P);
     const double *d_prec, *d_mt, *d_fr, *d_etp, *d_fice = nullptr;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(T * L), &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(T * L), &d_mt))) return rc;
@@ -1006,7 +1229,7 @@ int rrb_gr4j_simulate_multi(const double* prec, const double* etp, int64_t C, in
     if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
     if (N == 0 || C == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
-    HostDrain drain{P};
+    HostDrain drain(P);
     const double *d_prec, *d_etp, *d_inits;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(C * T), &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, etp, (size_t)(C * T), &d_etp))) return rc;
@@ -1029,7 +1252,7 @@ int rrb_gr4j_simulate_multi(const double* prec, const double* etp, int64_t C, in
     const std::vector<MultiOut> outs = {{qsim, T * N}, {s_store, T * N}, {r_store, T * N}};
     return run_multi(P, C, T, N, outs, [=](int64_t c0, int64_t c1, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
         Batch b{(int)(c1 - c0), fstride, T * N, d_inits + 4 * c0};
-        Slab slab{0, T, 0, nullptr, 0};
+        Slab slab{0, T, 0, nullptr, 0, 0};
         return launch_gr4j((const double*)F + c0 * fstride, T, 0.0, 0.0, dp + c0 * N * 4, N, x4_max, out[0], out[1], out[2],
                            slab, ob, cfg, b);
     });
@@ -1052,7 +1275,7 @@ int rrb_cemaneigegr4j_simulate_multi(const double* prec, const double* mean_temp
     if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
     if (N == 0 || C == 0) return RRB_OK;
     std::lock_guard<std::mutex> lk(P.c->mu);
-    HostDrain drain{P};
+    HostDrain drain(P);
     const double *d_prec, *d_mt, *d_fr, *d_etp, *d_inits;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(C * T * L), &d_prec))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(C * T * L), &d_mt))) return rc;
@@ -1077,7 +1300,7 @@ int rrb_cemaneigegr4j_simulate_multi(const double* prec, const double* mean_temp
     const double zero4[4] = {0, 0, 0, 0};
     return run_multi(P, C, T, N, outs, [=](int64_t c0, int64_t c1, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
         Batch b{(int)(c1 - c0), fstride, T * N, d_inits + 4 * c0};
-        Slab slab{0, T, 0, nullptr, 0};
+        Slab slab{0, T, 0, nullptr, 0, 0};
         return launch_cemaneigegr4j((const double*)F + c0 * fstride, (const double*)gt + c0 * 2 * kCemaMaxLayers, T, (int)L,
                                     zero4, dp + c0 * N * 6, N, x4_max, out[0], out[1], out[2], out[3], out[4], slab, ob,
                                     cfg, b);
@@ -1105,7 +1328,7 @@ int rrb_snow_layers(const double* prec, const double* mean_temp, const double* m
         k.high[l] = (flags[l] & RRB_LAYER_HIGH) != 0;
     }
     std::lock_guard<std::mutex> lk(P.c->mu);
-    HostDrain drain{P};
+    HostDrain drain(P);
     const double *d_p, *d_me, *d_mn, *d_mx;
     if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)T, &d_p))) return rc;
     if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)T, &d_me))) return rc;

@@ -148,9 +148,9 @@ cudaError_t launch_snow_layers(const double* prec, const double* mean_temp, cons
     return cudaGetLastError();
 }
 
-int state_slots_cemaneige(int L) { return 2 * layer_class(L) + 1; }
+int state_slots_cemaneige(int L) { return 2 * layer_class(L) + kObjSlots; }
 int state_slots_cemaneigegr4j(int L, double x4_max) {
-    return 2 * layer_class(L) + cema_uh_slots(cema_uh_class(x4_max)) + 1;
+    return 2 * layer_class(L) + cema_uh_slots(cema_uh_class(x4_max)) + kObjSlots;
 }
 
 cudaError_t launch_cemaneige(const double* F, const double* g_tresh, int64_t T, int L, double g0, double e0,

@@ -10,6 +10,7 @@
 #include "rr_common.cuh"
 #include "rr_gr4j.cuh"
 #include "rr_kernels.h"
+#include "rr_objective.cuh"
 
 namespace rrb {
 
@@ -87,6 +88,7 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
     const int64_t cb = (a.count > 1) ? (int64_t)blockIdx.y : 0;
     const bool WRITEQ = PLAIN || out.q != nullptr, STORAGE = !PLAIN && out.G != nullptr,
                OBJ = !PLAIN && obj.qobs != nullptr;  // CTA-uniform
+    if (obj.obs_stats) { obj.obs_mean = obj.obs_stats[2 * cb]; obj.obs_std = obj.obs_stats[2 * cb + 1]; }
     const double* __restrict__ F = a.F + cb * a.forcing_stride;
     const uint32_t* __restrict__ fflag =
         reinterpret_cast<const uint32_t*>(reinterpret_cast<const double*>(a.fflag) + cb * a.forcing_stride);
@@ -132,7 +134,8 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
     constexpr size_t kOrdOff = forcing_smem_bytes<R, TT>() + (HYST ? 0 : 32 * LC) + ((COUPLED && FAST) ? fastmath_smem_bytes() : 0);
     Gr4j gr;
     if constexpr (COUPLED) gr.init(p + GOFF, s_init, r_init, smem_u32(rrb_smem + kOrdOff));
-    double acc = 0.0;
+    ObjAcc acc;
+    acc.reset();
     constexpr int kLayerSlots = HYST ? 4 : 2;
     constexpr int kSlots = kLayerSlots * LC + Gr4j::kStateSlots;
     if (slab.t_begin > 0) {
@@ -146,7 +149,7 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
             }
         }
         if constexpr (COUPLED) gr.load(slab.state + (int64_t)kLayerSlots * LC * N, N, i);
-        if (OBJ) acc = slab.state[(int64_t)kSlots * N + i];
+        if (OBJ) acc.load(slab.state, kSlots, N, i, obj);
     }
     int64_t stride = N, strideL = (int64_t)L * N;
     pin(stride); pin(strideL);
@@ -213,8 +216,11 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
         // FAST path contract of Gr4jMember: finite, moderately ranged parameters, initial states and forcing --
         // then the snow routine feeds GR4J finite water.  CTA-uniform; the barrier also publishes the tables
         // (the peeled first step below already reads them).
+        // (hysteresis: Thacc == 0 -- the lower default bound, reachable by the polish step of fit() -- makes
+        // snow_balance / Thacc a NaN that the reference's max(0, NaN) = 0 absorbs; step_fast has no special-value
+        // handling, so such CTAs take the reference-order step: thacc_span != 0 <=> Thacc in [2^-60, 2^60])
         bool sane = gr.sane && *fflag == 0u && fabs(g0) <= 1e6 && fabs(e0) <= 1e6 && fabs(a.sca0) <= 1e6 &&
-                    (HYST || snow_ok);
+                    (HYST ? thacc_span != 0u : snow_ok);
         for (int k = 0; k < (int)a.pstride; ++k) sane = sane && fabs(p[k]) <= 1e6;
         if (ICE) {
 #pragma unroll
@@ -354,10 +360,7 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
                 sm_o += stride;
             }
         }
-        if (OBJ) {
-            const double d = qobs_c[t] - qv;
-            acc += d * d;
-        }
+        if (OBJ) acc.add(qobs_c[t], qv, obj);
     };
     auto step = [&](auto first_c, auto fast_c, auto snow_c, int64_t t, const double* f) {
         const SnowOut w = snow_part(first_c, snow_c, f);
@@ -407,9 +410,9 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
                 }
             }
             if constexpr (COUPLED) gr.save(slab.state + (int64_t)kLayerSlots * LC * N, N, i);
-            if (OBJ) slab.state[(int64_t)kSlots * N + i] = acc;
+            if (OBJ && slab.save_state == 1) acc.save(slab.state, kSlots, N, i, obj);
         }
-        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[cb * N + i] = acc / (double)obj.T;
+        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[cb * N + i] = acc.finish(obj);
     }
 }
 

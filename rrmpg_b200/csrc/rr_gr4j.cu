@@ -7,6 +7,7 @@
 #include "rr_common.cuh"
 #include "rr_gr4j.cuh"
 #include "rr_kernels.h"
+#include "rr_objective.cuh"
 
 namespace rrb {
 
@@ -61,6 +62,7 @@ __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double 
         if (qsim) qsim += c * batch.out_stride;
         if (s_store) { s_store += c * batch.out_stride; r_store += c * batch.out_stride; }
         if (obj.qobs) { obj.qobs += c * obj.T; obj.mse += c * N; }
+        if (obj.obs_stats) { obj.obs_mean = obj.obs_stats[2 * c]; obj.obs_std = obj.obs_stats[2 * c + 1]; }
     }
     if (batch.inits) {  // also for a batch (or a chunk of a batch) of ONE catchment
         const int64_t c = batch.count > 1 ? (int64_t)blockIdx.y : 0;
@@ -78,10 +80,11 @@ __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double 
     constexpr size_t kOrdOff = forcing_smem_bytes<kGr4jR, kGr4jTT>() + (FAST ? fastmath_smem_bytes() : 0);
     Member m;
     m.init(params + 4 * i, s_init, r_init, smem_u32(rrb_smem + kOrdOff));  // record = (x1, x2, x3, x4), gr4j.py:57-60
-    double acc = 0.0;
-    if (slab.t_begin > 0) {
+    ObjAcc acc;
+    acc.reset();
+    if (slab_loads_state(slab)) {
         m.load(slab.state, N, i);
-        if (OBJ) acc = slab.state[(int64_t)Member::kStateSlots * N + i];
+        if (OBJ && slab.t_begin > 0) acc.load(slab.state, Member::kStateSlots, N, i, obj);
     }
     int64_t stride = N;
     pin(stride);
@@ -121,10 +124,7 @@ __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double 
                         s_o += stride;
                         r_o += stride;
                     }
-                    if (OBJ) {
-                        const double d = obj.qobs[t0 + g] - qv;
-                        acc += d * d;
-                    }
+                    if (OBJ) acc.add(obj.qobs[t0 + g], qv, obj);
                 }
             });
     };
@@ -138,9 +138,9 @@ __global__ void gr4j_kernel(const double* __restrict__ F, double s_init, double 
     if (gi < N) {
         if (slab.save_state) {
             m.save(slab.state, N, i);
-            if (OBJ) slab.state[(int64_t)Member::kStateSlots * N + i] = acc;
+            if (OBJ && slab.save_state == 1) acc.save(slab.state, Member::kStateSlots, N, i, obj);
         }
-        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i] = acc / (double)obj.T;
+        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i] = acc.finish(obj);
     }
 }
 
@@ -155,10 +155,10 @@ static int uh_class(double x4_max) {
 
 int state_slots_gr4j(double x4_max) {
     switch (uh_class(x4_max)) {
-        case 0: return 2 + 3 + 7 + 1;
-        case 1: return 2 + 4 + 9 + 1;
-        case 2: return 2 + 10 + 21 + 1;
-        default: return Gr4jMemberDyn::kStateSlots + 1;
+        case 0: return 2 + 3 + 7 + kObjSlots;
+        case 1: return 2 + 4 + 9 + kObjSlots;
+        case 2: return 2 + 10 + 21 + kObjSlots;
+        default: return Gr4jMemberDyn::kStateSlots + kObjSlots;
     }
 }
 

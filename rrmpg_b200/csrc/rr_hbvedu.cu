@@ -20,11 +20,15 @@
 #include "rr_common.cuh"
 #include "rr_kernels.h"
 #include "rr_math.cuh"
+#include "rr_objective.cuh"
 
 #include <cstdlib>
 
 #ifndef RRB_HBV_DEFAULT_VARIANT
 #define RRB_HBV_DEFAULT_VARIANT 2
+#endif
+#ifndef RRB_HBV_PIPELINE
+#define RRB_HBV_PIPELINE 0
 #endif
 
 namespace rrb {
@@ -40,7 +44,9 @@ __global__ void hbv_pack_kernel(const double* __restrict__ temp, const double* _
     F += c * Tpad * kHbvR;
     double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
     if (t < T) {
-        const int m = month0[t];
+        // month index outside [0, 11]: the reference would read past PE_m / T_m (numba does no bounds checking);
+        // the Python layer validates host arrays, the kernel stays memory safe for any int8 a device caller passes
+        const int m = min(max((int)month0[t], 0), 11);
         v.x = temp[t];
         v.y = prec[t];
         v.z = temp[t] - T_m[m];
@@ -83,6 +89,7 @@ __device__ __forceinline__ uint32_t* hbv_cta_flags(uint32_t* fflag) { return ffl
             out.s1 += c * batch.out_stride; out.s2 += c * batch.out_stride;       \
         }                                                                         \
         if (obj.qobs) { obj.qobs += c * obj.T; obj.mse += c * N; }                \
+        if (obj.obs_stats) { obj.obs_mean = obj.obs_stats[2 * c]; obj.obs_std = obj.obs_stats[2 * c + 1]; } \
     }                                                                             \
     if (batch.inits) { /* also for a batch (or a chunk of a batch) of ONE catchment */ \
         const int64_t c = batch.count > 1 ? (int64_t)blockIdx.y : 0;              \
@@ -97,10 +104,6 @@ struct HbvF {  // forcing of one timestep
         return HbvF{a.x, a.y, b.x, b.y};
     }
 };
-
-// rare operands (soil/FC outside [2^-15, 2^15), |Beta| >= 32, FC <= 0, non-finite values): the reference's
-// own operations, out of line so they cost the time loop one predicated branch
-static __device__ __noinline__ double hbv_slow_pow(double soil, double FC, double Beta) { return pow(soil / FC, Beta); }
 
 // ------------------------------------------------------------------------------------------------
 // PRECISE: every operation of the reference, in the reference's order.
@@ -127,15 +130,16 @@ __global__ void hbv_precise_kernel(const double* __restrict__ F, double snow0, d
     const double K_0 = p[6], K_1 = p[7], K_2 = p[8], K_p = p[9], L = p[10];
 
     double snow = snow0, soil = soil0, s1 = s10, s2 = s20;  // hbvedu_model.py:78-81
-    double acc = 0.0;
+    ObjAcc acc;
+    acc.reset();
     int64_t t_first = slab.t_begin;
     int64_t off = i + (slab.t_begin - slab.row0) * N;  // row r of the buffers = timestep row0 + r
-    if (slab.t_begin > 0) {
+    if (slab_loads_state(slab)) {
         snow = slab.state[0 * N + i];
         soil = slab.state[1 * N + i];
         s1 = slab.state[2 * N + i];
         s2 = slab.state[3 * N + i];
-        if (OBJ) acc = slab.state[4 * N + i];
+        if (OBJ && slab.t_begin > 0) acc.load(slab.state, 4, N, i, obj);
     } else {
         // t = 0 is not simulated (the reference loop starts at 1, hbvedu_model.py:84): qsim[0] = 0 and the
         // storages hold the initial states
@@ -146,10 +150,7 @@ __global__ void hbv_precise_kernel(const double* __restrict__ F, double snow0, d
             st_stream(out.s1 + off, s1);
             st_stream(out.s2 + off, s2);
         }
-        if (OBJ) {
-            const double d = obj.qobs[0];
-            acc = d * d;
-        }
+        if (OBJ) acc.add(obj.qobs[0], 0.0, obj);
         off += N;
         t_first = 1;
     }
@@ -192,10 +193,7 @@ __global__ void hbv_precise_kernel(const double* __restrict__ F, double snow0, d
             s1_o += N;
             s2_o += N;
         }
-        if (OBJ) {
-            const double d = obj.qobs[t] - qv;
-            acc += d * d;
-        }
+        if (OBJ) acc.add(obj.qobs[t], qv, obj);
     });
 
     if (gi < N) {
@@ -204,188 +202,11 @@ __global__ void hbv_precise_kernel(const double* __restrict__ F, double snow0, d
             slab.state[1 * N + i] = soil;
             slab.state[2 * N + i] = s1;
             slab.state[3 * N + i] = s2;
-            if (OBJ) slab.state[4 * N + i] = acc;
+            if (OBJ && slab.save_state == 1) acc.save(slab.state, 4, N, i, obj);
         }
-        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i] = acc / (double)obj.T;
+        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i] = acc.finish(obj);
     }
 }
-
-// ------------------------------------------------------------------------------------------------
-// FAST: the same recurrence reorganised for the fp64 pipe and for the few warps per scheduler that a
-// 65 536-member ensemble leaves (one thread per member = 3.5 warps per SM sub-partition).
-//   A(t)  snow routine + potential evapotranspiration: needs forcing[t], snow[t-1] and parameters only
-//   B(t)  soil moisture (the pow), response routine, discharge: the long dependent chain
-// Timesteps are processed in groups of G: first A for the whole group (independent work, high ILP),
-// then one warp vote per step ("does any member have liquid water?", known without touching the soil
-// chain), then the B chains, each either with or without the pow.
-// ------------------------------------------------------------------------------------------------
-#ifndef RRB_HBV_GROUP
-#define RRB_HBV_GROUP 2
-#endif
-constexpr int kHbvGroup = RRB_HBV_GROUP;
-
-// Cost model (measured, profiles/r01_*): with one thread per member the 65 536-member workload leaves 3.5
-// warps per SM sub-partition and the kernel is ISSUE bound -- every fp64 instruction holds the issue port
-// for 2 cycles (16 fp64 lanes per sub-partition), every other instruction for 1.  The body below is written
-// to minimise (2 x fp64 + other) instructions per member-timestep: ~21 fp64 + ~22 other without the pow,
-// ~27 fp64 + ~11 other more with it (61.6 warp-instructions on average on the bench forcing, ncu).
-template <bool WRITEQ, bool STORAGE, bool OBJ>
-__global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
-                                const double* __restrict__ params, int64_t N, HbvOut out, Slab slab,
-                                Objective obj, Batch batch, const uint32_t* __restrict__ fflag) {
-    // FAST contract: finite precipitation and temperature (the snow routine below forms prec - prec for "no liquid
-    // water" and reads temp < T_t off the sign of temp - T_t).  The
-    // packer flags anything else and the PRECISE kernel launched right behind this one takes the whole launch.
-    if (*fflag != 0u) return;
-    HBV_BATCH_PROLOGUE
-    const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t i = gi < N ? gi : N - 1;  // see hbv_precise_kernel
-    const double* p = params + 11 * i;
-    const double T_t = p[0], DD = p[1], FC = p[2], Beta = p[3], C = p[4], PWP = p[5];
-    const double K_0 = p[6], K_1 = p[7], K_2 = p[8], K_p = p[9], L = p[10];
-    double inv_FC = 1.0 / FC, inv_PWP = 1.0 / PWP;
-    // max(0, s1 - L) is read off the sign bit below; numba's max(0, NaN) = 0 for a NaN threshold = an infinite one
-    const double Lq = (L == L) ? L : __longlong_as_double(0x7FF0000000000000LL);
-    // temp < T_t is read off the sign of temp - T_t: a NaN threshold of either sign means "never cold", like the
-    // reference's comparison (the subtraction then yields the canonical, positive NaN)
-    // ... and a zero threshold is taken as -0.0: temp - (-0.0) is +0 for temp = +-0, like the reference's -0.0 < 0.0 = False
-    const double Tt = (T_t == T_t) ? ((T_t == 0.0) ? -0.0 : T_t) : __longlong_as_double(0x7FF8000000000000LL);
-    double c1 = 1.0 - K_1 - K_p;  // s1 (1 - K_1 - K_p)
-    double c2 = 1.0 - K_2;        // s2 (1 - K_2)
-    // The table-driven pow is used when soil/FC is within [2^-15, 2^15) and |Beta| < 32 (then
-    // |Beta log2 x| < 512 and x is a positive normal).  The range test is one unsigned compare on the high
-    // word of soil against per-member bounds derived from FC (never true for FC <= 0, NaN, inf, denormal).
-    uint32_t safe_lo = 0u, safe_span = 0u;
-    if (fabs(Beta) < 32.0 && FC > 0x1p-900 && FC < 0x1p900) {
-        safe_lo = (uint32_t)__double2hiint(FC * 0x1p-15) + 1u;
-        safe_span = (uint32_t)__double2hiint(FC * 0x1p15) - safe_lo;
-    }
-    int64_t stride = N;
-    pin(inv_FC); pin(inv_PWP); pin(c1); pin(c2); pin(safe_lo); pin(safe_span); pin(stride);
-
-    double snow = snow0, soil = soil0, s1 = s10, s2 = s20;  // hbvedu_model.py:78-81
-    double acc = 0.0;
-    int64_t t_first = slab.t_begin;
-    int64_t off = i + (slab.t_begin - slab.row0) * N;
-    if (slab.t_begin > 0) {
-        snow = slab.state[0 * N + i];
-        soil = slab.state[1 * N + i];
-        s1 = slab.state[2 * N + i];
-        s2 = slab.state[3 * N + i];
-        if (OBJ) acc = slab.state[4 * N + i];
-    } else {
-        if (WRITEQ) st_stream(out.qsim + off, 0.0);
-        if (STORAGE) {
-            st_stream(out.snow + off, snow);
-            st_stream(out.soil + off, soil);
-            st_stream(out.s1 + off, s1);
-            st_stream(out.s2 + off, s2);
-        }
-        if (OBJ) {
-            const double d = obj.qobs[0];
-            acc = d * d;
-        }
-        off += N;
-        t_first = 1;
-    }
-    double* q_o = WRITEQ ? out.qsim + off : nullptr;
-    double* snow_o = STORAGE ? out.snow + off : nullptr;
-    double* soil_o = STORAGE ? out.soil + off : nullptr;
-    double* s1_o = STORAGE ? out.s1 + off : nullptr;
-    double* s2_o = STORAGE ? out.s2 + off : nullptr;
-
-    extern __shared__ __align__(128) unsigned char rrb_smem[];
-    uint32_t tb = smem_u32(fastmath_tables_to_smem(rrb_smem + forcing_smem_bytes<kHbvR, kHbvTT>()));
-    pin(tb);
-    __syncthreads();  // the staged tables are visible
-    const PowRegs pr = load_pow_regs(tb);
-
-    stream_forcing_grouped<kHbvR, kHbvTT, kHbvGroup, HbvF>(
-        F, t_first, slab.t_end, [&](auto gc, int64_t t0, const HbvF* f) {
-            constexpr int G = decltype(gc)::value;
-            double liquid[G], pe[G], snow_g[G];
-            bool need[G];
-            // ---- A: snow routine (hbvedu_model.py:87-96), potential evapotranspiration (:102).
-            // Both branches are evaluated and selected.  max(0, snow - m) and min(snow, m) share one
-            // predicate: snow - m > 0 <=> m < snow for every operand pair (NaN and inf included).
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                // melt = min(snow, DD (temp - T_t)) serves both max(0, snow - m) = snow - melt and the liquid water
-                // prec + melt; the cold branch (snow + prec, no liquid water) is the same two additions with
-                // -prec in place of melt: snow - (-prec) and prec + (-prec) = +0 for finite precipitation
-                const double dtt = f[g].temp - Tt;
-                const double m = DD * dtt;
-                const double melt = (m < snow) ? m : snow;
-                const bool cold = __double2hiint(dtt) < 0;  // temp < T_t through the sign of the (finite) difference
-                const double nprec = __hiloint2double(__double2hiint(f[g].prec) ^ (int)0x80000000, __double2loint(f[g].prec));
-                const double sel = cold ? nprec : melt;
-                snow = snow - sel;
-                liquid[g] = f[g].prec + sel;
-                snow_g[g] = snow;
-                pe[g] = fma(C, f[g].dT, f[g].PEm);  // FAST packing: dT holds dT * PEm
-            }
-            // ---- prec_eff = liquid * (soil/FC)^Beta (:99) is +0 whenever liquid == 0 and the power is
-            // finite, so a warp evaluates the pow only if one of its members has liquid water
-#pragma unroll
-            for (int g = 0; g < G; ++g)  // liquid != 0 on the bit pattern (one LOP3; -0 and NaN count as water)
-                need[g] = __any_sync(0xffffffffu, (__double2hiint(liquid[g]) | __double2loint(liquid[g])) != 0);
-            // ---- B: soil moisture, response routine, discharge
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const bool safe = ((uint32_t)__double2hiint(soil) - safe_lo) < safe_span;
-                const double ea = (soil > PWP) ? pe[g] : pe[g] * (soil * inv_PWP);  // :105-108
-                const double oK = max0_sane(s1 - Lq) * K_0;  // sign-bit select: a NaN s1 poisons s1_new and q either way
-                const double s2_new = fma(s1, K_p, s2 * c2);                         // :121-123
-                double s1_new = fma(s1, c1, -oK);                                    // :114-118 without prec_eff
-                double soil_new = (soil + liquid[g]) - ea;                           // :111 without prec_eff
-                if (need[g]) {
-                    double pw = fast_pow_unchecked_smem(soil * inv_FC, Beta, tb, pr);
-                    if (!safe) pw = hbv_slow_pow(soil, FC, Beta);
-                    const double prec_eff = liquid[g] * pw;
-                    soil_new -= prec_eff;
-                    s1_new += prec_eff;
-                } else if (!safe) {
-                    const double prec_eff = liquid[g] * hbv_slow_pow(soil, FC, Beta);  // 0 * (inf | nan)
-                    soil_new -= prec_eff;
-                    s1_new += prec_eff;
-                }
-                soil = soil_new;
-                s1 = s1_new;
-                s2 = s2_new;
-                const double qv = fma(s2_new, K_2, fma(s1_new, K_1, oK));            // :125-127
-                if (WRITEQ) {
-                    st_stream(q_o, qv);
-                    q_o += stride;
-                }
-                if (STORAGE) {
-                    st_stream(snow_o, snow_g[g]);
-                    st_stream(soil_o, soil);
-                    st_stream(s1_o, s1);
-                    st_stream(s2_o, s2);
-                    snow_o += stride;
-                    soil_o += stride;
-                    s1_o += stride;
-                    s2_o += stride;
-                }
-                if (OBJ) {
-                    const double d = obj.qobs[t0 + g] - qv;
-                    acc += d * d;
-                }
-            }
-        });
-
-    if (gi < N) {
-        if (slab.save_state) {
-            slab.state[0 * N + i] = snow;
-            slab.state[1 * N + i] = soil;
-            slab.state[2 * N + i] = s1;
-            slab.state[3 * N + i] = s2;
-            if (OBJ) slab.state[4 * N + i] = acc;
-        }
-        if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i] = acc / (double)obj.T;
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------------
 // FAST, round 2 (hbv_fast2_kernel): organised for the DEPTH of the loop-carried soil chain.
@@ -408,11 +229,15 @@ __global__ void hbv_fast_kernel(const double* __restrict__ F, double snow0, doub
 // FAST contract per member (else the CTA is left to PRECISE): all parameters and initial states finite, FC and PWP in
 // [2^-500, 2^500], |Beta| < 32.  Per launch (forcing flag, set by the packer): finite precipitation and temperature.
 // ------------------------------------------------------------------------------------------------
+constexpr int kHbvGroup = 2;  // timesteps per group of the software pipeline
+
 struct HbvPowK {  // polynomial coefficients held in registers (an FMA takes one constant-bank operand)
     double a1, a2, a3, a4, c1, c2, c3;
 };
 
-template <int MPT, bool WRITEQ, bool STORAGE, bool OBJ>
+// ABL: timing ablations for the discharge-only instantiation (development builds only, results are WRONG):
+//   1 no output stores, 2 never wet, 3 always wet, 4 table loads replaced by constants
+template <int MPT, bool WRITEQ, bool STORAGE, bool OBJ, int ABL = 0>
 __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                                  const double* __restrict__ params, int64_t N, HbvOut out, Slab slab, Objective obj,
                                  Batch batch, uint32_t* __restrict__ fflag) {
@@ -451,23 +276,24 @@ __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, dou
     sane = sane && fabs(snow0) <= 1e300 && fabs(soil0) <= 1e300 && fabs(s10) <= 1e300 && fabs(s20) <= 1e300;
     uint32_t* my_flag = hbv_cta_flags(fflag) + (blockIdx.y * gridDim.x + blockIdx.x);
     if (!__syncthreads_and(sane)) {  // CTA-uniform: a member outside the contract
-        if (threadIdx.x == 0) *my_flag = 1u;
+        *my_flag = 1u;               // (every thread stores the same word: no divergent region in front of the warp votes)
         return;
     }
 
-    double snow[MPT], soil[MPT], s1[MPT], s2[MPT], acc[MPT];
+    double snow[MPT], soil[MPT], s1[MPT], s2[MPT];
+    ObjAcc acc[MPT];
 #pragma unroll
-    for (int m = 0; m < MPT; ++m) { snow[m] = snow0; soil[m] = soil0; s1[m] = s10; s2[m] = s20; acc[m] = 0.0; }  // hbvedu_model.py:78-81
+    for (int m = 0; m < MPT; ++m) { snow[m] = snow0; soil[m] = soil0; s1[m] = s10; s2[m] = s20; acc[m].reset(); }  // hbvedu_model.py:78-81
     int64_t t_first = slab.t_begin;
     int64_t off = i0 + (slab.t_begin - slab.row0) * N;  // row r of the buffers = timestep row0 + r
-    if (slab.t_begin > 0) {
+    if (slab_loads_state(slab)) {
 #pragma unroll
         for (int m = 0; m < MPT; ++m) {
             snow[m] = slab.state[0 * N + i0 + m];
             soil[m] = slab.state[1 * N + i0 + m];
             s1[m] = slab.state[2 * N + i0 + m];
             s2[m] = slab.state[3 * N + i0 + m];
-            if (OBJ) acc[m] = slab.state[4 * N + i0 + m];
+            if (OBJ && slab.t_begin > 0) acc[m].load(slab.state, 4, N, i0 + m, obj);
         }
     } else {
         // t = 0 is not simulated (the reference loop starts at 1, hbvedu_model.py:84): qsim[0] = 0, storages = initial states
@@ -480,10 +306,7 @@ __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, dou
                 st_stream(out.s1 + off + m, s1[m]);
                 st_stream(out.s2 + off + m, s2[m]);
             }
-            if (OBJ) {
-                const double d = obj.qobs[0];
-                acc[m] = d * d;
-            }
+            if (OBJ) acc[m].add(obj.qobs[0], 0.0, obj);
         }
         off += N;
         t_first = 1;
@@ -496,9 +319,11 @@ __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, dou
     uint32_t row_bytes = (uint32_t)N * 8u;  // N < 2^29 (launch_hbvedu)
     uint32_t row = 0u;                      // rows written since t_first
     pin(row_bytes);
-    auto put = [&](char* base, uint32_t r, const double* v) {
+    auto put = [&](char* base, uint32_t r, const double* v) __attribute__((always_inline)) {
         double* p = reinterpret_cast<double*>(base + (uint64_t)r * (uint64_t)row_bytes);  // IMAD.WIDE.U32
-        if (MPT == 2) st_stream_pair(p, v[0], v[MPT - 1]);
+        if constexpr (ABL == 1) {
+            if (v[0] == 1.2345e-300) st_stream(p, v[MPT - 1]);  // keeps the value alive, (almost) never stores
+        } else if (MPT == 2) st_stream_pair(p, v[0], v[MPT - 1]);
         else st_stream(p, v[0]);
     };
 
@@ -510,110 +335,213 @@ __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, dou
     const HbvPowK pk{lds_f64_at(pa), lds_f64_at(pa + 8), lds_f64_at(pa + 16), lds_f64_at(pa + 24),
                      lds_f64_at(pa + 32), lds_f64_at(pa + 40), lds_f64_at(pa + 48)};
 
-    stream_forcing_grouped<kHbvR, kHbvTT, kHbvGroup, HbvF>(
-        F, t_first, slab.t_end, [&](auto gc, int64_t t0, const HbvF* f) {
-            constexpr int G = decltype(gc)::value;
-            double liquid[G][MPT], pe[G][MPT], pew[G][MPT], snow_g[G][MPT];
-            bool need[G];
-            // ---- A: snow routine (hbvedu_model.py:87-96), potential evapotranspiration (:102); off the soil chain.
-            // melt = min(snow, DD (temp - T_t)) serves both max(0, snow - m) = snow - melt and the liquid water
-            // prec + melt; the cold branch (snow + prec, no liquid water) is the same two additions with -prec in
-            // place of melt: snow - (-prec) and prec + (-prec) = +0 for finite precipitation
+    // ---- the time loop: groups of two timesteps, software-pipelined by one group, four straight-line bodies.
+    // A(t): snow routine (hbvedu_model.py:87-96) and potential evapotranspiration (:102) -- needs forcing[t], the snow pack
+    //       and parameters only: short chains, independent of the soil / response stores.
+    // B(t): soil moisture (:99-111), response routine (:114-123), discharge (:125-127) -- the loop-carried chains.
+    // A warp issues in order, so a basic block runs at the latency of its longest dependent chain unless it holds enough
+    // independent work, and with 2-4 warps per SM sub-partition nothing else hides that latency (profiles/r02_*).  The
+    // pow of B(t) is a ~190-cycle chain that is skipped when no member of the warp has liquid water (warp vote); a branch
+    // per step would cut the loop body into short blocks, each as slow as its own chain.  So the vote of BOTH steps of a
+    // group is taken first (in the A phase, one group ahead) and selects one of four bodies -- (wet|dry, wet|dry) -- each
+    // a single basic block holding B of the two steps and A of the next group, which the scheduler interleaves.
+    static_assert(kHbvGroup == 2, "the four group bodies are written for two timesteps per group");
+    constexpr int GP = 2;
+    struct AOut {
+        double liquid[GP][MPT], pe[GP][MPT], pew[GP][MPT], snow_g[GP][MPT];
+        bool need[GP];
+    };
+    AOut cur;             // A results of the group whose B phase runs next
+    int64_t t_cur = 0;    // first timestep of `cur`
+    bool pending = false; // `cur` holds A results whose B phase has not run yet
+
+    auto phase_a = [&](const HbvF& f, AOut& o, int g) __attribute__((always_inline)) {
+        // melt = min(snow, DD (temp - T_t)) serves both max(0, snow - m) = snow - melt and the liquid water prec + melt;
+        // the cold branch (snow + prec, no liquid water) is the same two additions with -prec in place of melt:
+        // snow - (-prec) and prec + (-prec) = +0 for finite precipitation
+        const double nprec = __hiloint2double(__double2hiint(f.prec) ^ (int)0x80000000, __double2loint(f.prec));
+        bool wet = false;
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const double nprec = __hiloint2double(__double2hiint(f[g].prec) ^ (int)0x80000000, __double2loint(f[g].prec));
-                bool wet = false;
+        for (int m = 0; m < MPT; ++m) {
+            const double dtt = f.temp - Tt[m];
+            const double mm = DD[m] * dtt;
+            const double melt = (mm < snow[m]) ? mm : snow[m];
+            const bool cold = __double2hiint(dtt) < 0;  // temp < T_t through the sign of the (finite) difference
+            const double sel = cold ? nprec : melt;
+            snow[m] = snow[m] - sel;
+            o.liquid[g][m] = f.prec + sel;
+            o.snow_g[g][m] = snow[m];
+            o.pe[g][m] = fma(C[m], f.dT, f.PEm);  // FAST packing: dT holds dT * PEm
+            o.pew[g][m] = o.pe[g][m] * inv_PWP[m];
+            wet = wet || ((__double2hiint(o.liquid[g][m]) | __double2loint(o.liquid[g][m])) != 0);  // -0 and NaN count as water
+        }
+        // prec_eff = liquid * (soil/FC)^Beta (:99) is +0 whenever liquid == 0 and the power is finite, so a warp
+        // evaluates the pow only if one of its members has liquid water
+        o.need[g] = __any_sync(0xffffffffu, wet);
+        if constexpr (ABL == 2) o.need[g] = false;
+        if constexpr (ABL == 3) o.need[g] = true;
+    };
+    // B of step g of group `a`; WET = the warp evaluates the pow for this step
+    auto phase_b = [&](auto wet_c, const AOut& a, int g) __attribute__((always_inline)) {
+        constexpr bool WET = decltype(wet_c)::value != 0;
+        double qv[MPT], sp[MPT], oK[MPT], s1_new[MPT], s2_new[MPT];
+        uint32_t hs[MPT];
 #pragma unroll
-                for (int m = 0; m < MPT; ++m) {
-                    const double dtt = f[g].temp - Tt[m];
-                    const double mm = DD[m] * dtt;
-                    const double melt = (mm < snow[m]) ? mm : snow[m];
-                    const bool cold = __double2hiint(dtt) < 0;  // temp < T_t through the sign of the (finite) difference
-                    const double sel = cold ? nprec : melt;
-                    snow[m] = snow[m] - sel;
-                    liquid[g][m] = f[g].prec + sel;
-                    snow_g[g][m] = snow[m];
-                    pe[g][m] = fma(C[m], f[g].dT, f[g].PEm);  // FAST packing: dT holds dT * PEm
-                    pew[g][m] = pe[g][m] * inv_PWP[m];
-                    wet = wet || ((__double2hiint(liquid[g][m]) | __double2loint(liquid[g][m])) != 0);  // -0 and NaN count as water
-                }
-                // prec_eff = liquid * (soil/FC)^Beta (:99) is +0 whenever liquid == 0 and the power is finite, so a warp
-                // evaluates the pow only if one of its members has liquid water
-                need[g] = __any_sync(0xffffffffu, wet);
+        for (int m = 0; m < MPT; ++m) {
+            hs[m] = (uint32_t)__double2hiint(soil[m]);
+            worst[m] = max(worst[m], hs[m] - safe_lo[m]);  // sticky range check, judged after the time loop
+            const double ea = (soil[m] > PWP[m]) ? a.pe[g][m] : a.pew[g][m] * soil[m];  // :105-108
+            sp[m] = (soil[m] + a.liquid[g][m]) - ea;                                     // :111 without prec_eff
+            oK[m] = max0_sane(s1[m] - Lq[m]) * K_0[m];
+            s2_new[m] = fma(s1[m], K_p[m], s2[m] * c2[m]);                               // :121-123
+            s1_new[m] = fma(s1[m], c1[m], -oK[m]);                                       // :114-118 without prec_eff
+        }
+        if constexpr (WET) {
+            // written stage by stage ACROSS the members so that the instruction order handed to the assembler already
+            // interleaves their chains
+            using namespace hbvpow;
+            double mant[MPT], invc[MPT], log2c[MPT], kml[MPT], r[MPT], Lg[MPT], kd[MPT], rr[MPT], scale[MPT], w[MPT];
+            uint32_t ki[MPT], tlo[MPT], thi[MPT];
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) {  // log2(soil) - log2(FC): table lookup keyed on the top 9 mantissa bits
+                if constexpr (ABL == 4) { invc[m] = pk.a1 + (double)(hs[m] >> 7); log2c[m] = pk.a2; }
+                else
+                asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc[m]), "=d"(log2c[m]) : "r"(tb + ((hs[m] >> 7) & 0x1FF0u)));
+                mant[m] = __hiloint2double((int)((hs[m] & 0x000FFFFFu) | 0x3FF00000u), __double2loint(soil[m]));
+                kml[m] = (double)((int)(hs[m] >> 20) - 1023) - log2FC[m];
             }
-            // ---- B: soil moisture, response routine, discharge
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                double qv[MPT], sp[MPT], oK[MPT], s1_new[MPT], s2_new[MPT];
-                uint32_t hs[MPT];
+            for (int m = 0; m < MPT; ++m) r[m] = fma(mant[m], invc[m], -1.0);
 #pragma unroll
-                for (int m = 0; m < MPT; ++m) {
-                    hs[m] = (uint32_t)__double2hiint(soil[m]);
-                    worst[m] = max(worst[m], hs[m] - safe_lo[m]);  // sticky range check, judged after the time loop
-                    const double ea = (soil[m] > PWP[m]) ? pe[g][m] : pew[g][m] * soil[m];  // :105-108
-                    sp[m] = (soil[m] + liquid[g][m]) - ea;                                   // :111 without prec_eff
-                    oK[m] = max0_sane(s1[m] - Lq[m]) * K_0[m];
-                    s2_new[m] = fma(s1[m], K_p[m], s2[m] * c2[m]);                           // :121-123
-                    s1_new[m] = fma(s1[m], c1[m], -oK[m]);                                   // :114-118 without prec_eff
-                }
-                if (need[g]) {  // warp-uniform; the chains of the thread's members share one basic block and interleave
-                    using namespace hbvpow;
+            for (int m = 0; m < MPT; ++m) {
+                const double base = kml[m] + log2c[m];
+                const double r2 = r[m] * r[m];
+                const double pa = fma(r[m], pk.a2, pk.a1);
+                const double pb = fma(r[m], pk.a4, pk.a3);
+                const double t = fma(r2, pb, pa);
+                Lg[m] = fma(r[m], t, base);
+            }
 #pragma unroll
-                    for (int m = 0; m < MPT; ++m) {
-                        // log2(soil) - log2(FC)
-                        const double mant = __hiloint2double((int)((hs[m] & 0x000FFFFFu) | 0x3FF00000u), __double2loint(soil[m]));
-                        double invc, log2c;
-                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(log2c) : "r"(tb + ((hs[m] >> 7) & 0x1FF0u)));
-                        const double kml = (double)((int)(hs[m] >> 20) - 1023) - log2FC[m];
-                        const double r = fma(mant, invc, -1.0);
-                        const double base = kml + log2c;
-                        const double r2 = r * r;
-                        const double a = fma(r, pk.a2, pk.a1);
-                        const double b = fma(r, pk.a4, pk.a3);
-                        const double t = fma(r2, b, a);
-                        const double Lg = fma(r, t, base);
-                        // 2^(Beta Lg) = scale (1 + rr gg)
-                        const double kd = fma(Beta[m], Lg, kShift);
-                        const uint32_t ki = (uint32_t)__double2loint(kd);
-                        uint32_t tlo, thi;
-                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
-                                     : "=r"(tlo), "=r"(thi)
-                                     : "r"(tb + (uint32_t)offsetof(HbvTables, exp2k) + ((ki & (uint32_t)(tables::kExpKN - 1)) << 3)));
-                        const double kdm = kd - kShift;
-                        const double rr = fma(Beta[m], Lg, -kdm);
-                        const double scale = __hiloint2double((int)(thi + (ki << 10)), (int)tlo);  // bits + (ki << 42)
-                        const double q2 = rr * rr;
-                        const double e = fma(rr, pk.c2, pk.c1);
-                        const double gg = fma(q2, pk.c3, e);
-                        const double u = rr * gg;
-                        const double w = fma(liquid[g][m], u, liquid[g][m]);
-                        soil[m] = fma(-scale, w, sp[m]);
-                        s1_new[m] += scale * w;
-                    }
+            for (int m = 0; m < MPT; ++m) {  // 2^(Beta Lg) = scale (1 + rr gg)
+                kd[m] = fma(Beta[m], Lg[m], kShift);
+                ki[m] = (uint32_t)__double2loint(kd[m]);
+                if constexpr (ABL == 4) { tlo[m] = ki[m] & 1023u; thi[m] = 0x3FF00000u; }
+                else
+                asm("ld.shared.v2.u32 {%0, %1}, [%2];"
+                    : "=r"(tlo[m]), "=r"(thi[m])
+                    : "r"(tb + (uint32_t)offsetof(HbvTables, exp2k) + ((ki[m] & (uint32_t)(tables::kExpKN - 1)) << 3)));
+            }
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) {
+                const double kdm = kd[m] - kShift;
+                rr[m] = fma(Beta[m], Lg[m], -kdm);
+                scale[m] = __hiloint2double((int)(thi[m] + (ki[m] << 10)), (int)tlo[m]);  // bits + (ki << 42)
+            }
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) {
+                const double q2 = rr[m] * rr[m];
+                const double e = fma(rr[m], pk.c2, pk.c1);
+                const double gg = fma(q2, pk.c3, e);
+                const double u = rr[m] * gg;
+                w[m] = fma(a.liquid[g][m], u, a.liquid[g][m]);
+            }
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) {
+                soil[m] = fma(-scale[m], w[m], sp[m]);
+                s1_new[m] += scale[m] * w[m];
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) soil[m] = sp[m];
+        }
+#pragma unroll
+        for (int m = 0; m < MPT; ++m) {
+            s1[m] = s1_new[m];
+            s2[m] = s2_new[m];
+            qv[m] = fma(s2_new[m], K_2[m], fma(s1_new[m], K_1[m], oK[m]));               // :125-127
+            if (OBJ) acc[m].add(obj.qobs[t_cur + g], qv[m], obj);
+        }
+        if (WRITEQ) put(q_o, row, qv);
+        if (STORAGE) {
+            put(snow_o, row, a.snow_g[g]);
+            put(soil_o, row, soil);
+            put(s1_o, row, s1);
+            put(s2_o, row, s2);
+        }
+        ++row;
+    };
+    // B of both steps of the group in `cur`: one of four straight-line bodies, selected by the two warp votes
+    auto run_group_b = [&]() __attribute__((always_inline)) {
+        if (cur.need[0]) {
+            if (cur.need[1]) { phase_b(ic<1>{}, cur, 0); phase_b(ic<1>{}, cur, 1); }
+            else             { phase_b(ic<1>{}, cur, 0); phase_b(ic<0>{}, cur, 1); }
+        } else {
+            if (cur.need[1]) { phase_b(ic<0>{}, cur, 0); phase_b(ic<1>{}, cur, 1); }
+            else             { phase_b(ic<0>{}, cur, 0); phase_b(ic<0>{}, cur, 1); }
+        }
+    };
+#if RRB_HBV_PIPELINE
+    // software-pipelined form: A of the next group inside every body (more overlap, more instructions: measured equal)
+    auto body = [&](auto w0, auto w1, auto next_c, const HbvF* fn) __attribute__((always_inline)) {
+        constexpr bool NEXT = decltype(next_c)::value != 0;
+        AOut nx;
+        if constexpr (NEXT) {
+            phase_a(fn[0], nx, 0);
+            phase_a(fn[1], nx, 1);
+        }
+        phase_b(w0, cur, 0);
+        phase_b(w1, cur, 1);
+        if constexpr (NEXT) cur = nx;
+    };
+    auto run_group = [&](auto next_c, const HbvF* fn) __attribute__((always_inline)) {
+        if (cur.need[0]) {
+            if (cur.need[1]) body(ic<1>{}, ic<1>{}, next_c, fn);
+            else body(ic<1>{}, ic<0>{}, next_c, fn);
+        } else {
+            if (cur.need[1]) body(ic<0>{}, ic<1>{}, next_c, fn);
+            else body(ic<0>{}, ic<0>{}, next_c, fn);
+        }
+    };
+#endif
+
+    stream_forcing_grouped<kHbvR, kHbvTT, kHbvGroup, HbvF>(
+        F, t_first, slab.t_end, [&](auto gc, int64_t t0, const HbvF* f) __attribute__((always_inline)) {
+            constexpr int G = decltype(gc)::value;
+            if constexpr (G == GP) {
+#if RRB_HBV_PIPELINE
+                if (pending) {
+                    run_group(ic<1>{}, f);
                 } else {
-#pragma unroll
-                    for (int m = 0; m < MPT; ++m) soil[m] = sp[m];
+                    phase_a(f[0], cur, 0);
+                    phase_a(f[1], cur, 1);
+                    pending = true;
                 }
-#pragma unroll
-                for (int m = 0; m < MPT; ++m) {
-                    s1[m] = s1_new[m];
-                    s2[m] = s2_new[m];
-                    qv[m] = fma(s2_new[m], K_2[m], fma(s1_new[m], K_1[m], oK[m]));           // :125-127
-                    if (OBJ) {
-                        const double d = obj.qobs[t0 + g] - qv[m];
-                        acc[m] += d * d;
-                    }
+                t_cur = t0;
+#else
+                phase_a(f[0], cur, 0);   // A of both steps: four independent short chains per member pair
+                phase_a(f[1], cur, 1);
+                t_cur = t0;
+                run_group_b();
+#endif
+            } else {  // a ragged step at the edge of a time slab
+#if RRB_HBV_PIPELINE
+                if (pending) {
+                    run_group(ic<0>{}, f);
+                    pending = false;
                 }
-                if (WRITEQ) put(q_o, row, qv);
-                if (STORAGE) {
-                    put(snow_o, row, snow_g[g]);
-                    put(soil_o, row, soil);
-                    put(s1_o, row, s1);
-                    put(s2_o, row, s2);
-                }
-                ++row;
+#endif
+                phase_a(f[0], cur, 0);
+                t_cur = t0;
+                if (cur.need[0]) phase_b(ic<1>{}, cur, 0);
+                else phase_b(ic<0>{}, cur, 0);
             }
         });
+#if RRB_HBV_PIPELINE
+    if (pending) run_group(ic<0>{}, nullptr);
+#else
+    (void)pending;
+    (void)run_group_b;
+#endif
 
     // did any soil moisture leave the range of the table-driven pow?  Then this CTA's results are void: flag it for
     // the PRECISE kernel behind and leave the carry state / objective as they were.
@@ -631,17 +559,17 @@ __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, dou
                 slab.state[1 * N + i0 + m] = soil[m];
                 slab.state[2 * N + i0 + m] = s1[m];
                 slab.state[3 * N + i0 + m] = s2[m];
-                if (OBJ) slab.state[4 * N + i0 + m] = acc[m];
+                if (OBJ && slab.save_state == 1) acc[m].save(slab.state, 4, N, i0 + m, obj);
             }
-            if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i0 + m] = acc[m] / (double)obj.T;
+            if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i0 + m] = acc[m].finish(obj);
         }
     }
 }
 
-int state_slots_hbvedu() { return 5; }
+int state_slots_hbvedu() { return 4 + kObjSlots; }
 
-// Which FAST kernel runs: 1 / 2 = hbv_fast2_kernel with one / two members per thread (round 2), 0 = the round-1
-// kernel (kept for A/B timing).  Default: two members per thread when the rows allow 16-byte stores.
+// Which FAST instantiation runs: hbv_fast2_kernel with one (1) or two (2) members per thread; rrb_opts.variant or the
+// environment variable RRMPG_B200_HBV_VARIANT override the default (A/B timing).
 static int hbv_variant() {
     static const int v = [] {
         const char* e = getenv("RRMPG_B200_HBV_VARIANT");
@@ -659,11 +587,11 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
     const bool fast = cfg.math == RRB_MATH_FAST_;
     const bool st = snow != nullptr, ob = obj.qobs != nullptr, wq = qsim != nullptr;
     HbvOut out{qsim, snow, soil, s1, s2};
-    int variant = cfg.variant > 0 ? (cfg.variant == 3 ? 0 : cfg.variant) : hbv_variant();
+    int variant = cfg.variant > 0 ? (cfg.variant & 15) : hbv_variant();
     auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) % 16) == 0; };
     const bool pair_ok = (N % 2) == 0 && aligned16(qsim) && aligned16(snow) && aligned16(soil) && aligned16(s1) && aligned16(s2) &&
                          (!slab.state || aligned16(slab.state));
-    if (variant < 0) variant = RRB_HBV_DEFAULT_VARIANT;
+    if (variant != 1 && variant != 2) variant = RRB_HBV_DEFAULT_VARIANT;
     if (variant == 2 && !pair_ok) variant = 1;
     const int mpt = (fast && variant == 2) ? 2 : 1;
     const int64_t nthreads = (N + mpt - 1) / mpt;
@@ -691,15 +619,19 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
         return cudaGetLastError();
     }
     uint32_t* wflag = const_cast<uint32_t*>(fflag);
-    if (variant == 0) {
-        const size_t smem = smem_ring + fastmath_smem_bytes();
-#define RRB_HBV_FAST1(Q_, S_, O_) hbv_fast_kernel<Q_, S_, O_><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, fflag)
-        RRB_HBV_DISPATCH(RRB_HBV_FAST1);
-#undef RRB_HBV_FAST1
-    } else {
+    {
         const size_t smem = smem_ring + hbv_tables_smem_bytes();
 #define RRB_HBV_FAST2A(Q_, S_, O_) hbv_fast2_kernel<1, Q_, S_, O_><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag)
 #define RRB_HBV_FAST2B(Q_, S_, O_) hbv_fast2_kernel<2, Q_, S_, O_><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag)
+#ifdef RRB_HBV_ABLATIONS
+        const int abl = cfg.variant / 16;
+        if (abl > 0 && wq && !st && !ob) {
+#define RRB_HBV_ABL(M_, A_) hbv_fast2_kernel<M_, true, false, false, A_><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag)
+            if (mpt == 2) { if (abl == 1) RRB_HBV_ABL(2, 1); else if (abl == 2) RRB_HBV_ABL(2, 2); else if (abl == 3) RRB_HBV_ABL(2, 3); else RRB_HBV_ABL(2, 4); }
+            else { if (abl == 1) RRB_HBV_ABL(1, 1); else if (abl == 2) RRB_HBV_ABL(1, 2); else if (abl == 3) RRB_HBV_ABL(1, 3); else RRB_HBV_ABL(1, 4); }
+#undef RRB_HBV_ABL
+        } else
+#endif
         if (mpt == 2) RRB_HBV_DISPATCH(RRB_HBV_FAST2B);
         else RRB_HBV_DISPATCH(RRB_HBV_FAST2A);
 #undef RRB_HBV_FAST2A

@@ -15,8 +15,12 @@ struct Slab {
     int64_t t_end;
     int64_t row0;
     double* state;
-    int save_state;
+    int save_state;  // 0 = no, 1 = all rows incl. the objective sums (internal carry buffer), 2 = model rows only (state_out)
+    int resume;  // the series continues an earlier call (rrb_opts.state_in): the states are loaded from `state` although
+                 // t_begin == 0, and timestep 0 is an ordinary step (ABC / HBV-Edu do not simulate t = 0 otherwise)
 };
+// true when the kernel starts from carried states instead of the initial ones
+__host__ __device__ inline bool slab_loads_state(const Slab& s) { return s.t_begin > 0 || s.resume != 0; }
 
 // Catchment batching: blockIdx.y selects one of `count` independent catchments that share T and the
 // number of members N.  Element strides (in doubles) between consecutive catchments; count = 1 and zero
@@ -37,14 +41,19 @@ struct LaunchCfg {
     int variant;  // rrb_opts.variant (0 = default)
 };
 
-// fused per-member objective: when qobs != nullptr the kernels accumulate
-// sum_t (qobs[t] - q[t])^2 in a register (rrmpg/tools/monte_carlo.py:70-71 +
-// rrmpg/utils/metrics.py:131; carried across slabs through `state`) and the last slab writes
-// mse[i] = sum / T.
+// fused per-member objective (rr_objective.cuh): when qobs != nullptr the kernels accumulate the sums of the chosen
+// metric in registers (carried across time slabs through kObjSlots rows of `state`, behind the model's own rows) and
+// the launch whose slab ends at T writes mse[i] = the metric of member i.
+enum { RRB_OBJ_MSE_ = 0, RRB_OBJ_NSE_ = 1, RRB_OBJ_KGE_ = 2 };
+constexpr int kObjSlots = 4;
 struct Objective {
     const double* qobs;  // [T] device, nullable
     double* mse;         // [N] device: written by the launch whose slab ends at T
     int64_t T;           // total series length (the divisor of np.mean)
+    int kind;            // RRB_OBJ_*_
+    double obs_mean;     // np.mean(qobs)  (NSE / KGE)
+    double obs_std;      // np.std(qobs), population standard deviation  (NSE / KGE)
+    const double* obs_stats;  // catchment batches: device [count][2] = (mean, std) per catchment (nullable)
 };
 
 int pick_block(int64_t N, int sm_count, int max_block);

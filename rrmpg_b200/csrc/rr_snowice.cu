@@ -13,7 +13,7 @@ cudaError_t launch_snowice_f2(const CemaArgs&, double, const CemaOut&, const Sla
 cudaError_t launch_snowice_f3(const CemaArgs&, double, const CemaOut&, const Slab&, const Objective&, const LaunchCfg&);
 
 int state_slots_snowice(int family, int L, double x4_max) {
-    return ((family & 1) ? 4 : 2) * cema_layer_class(L) + cema_uh_slots(cema_uh_class(x4_max)) + 1;
+    return ((family & 1) ? 4 : 2) * cema_layer_class(L) + cema_uh_slots(cema_uh_class(x4_max)) + kObjSlots;
 }
 
 cudaError_t launch_snowice(int family, const double* F, const double* g_tresh, const double* frac_ice, int64_t T, int L,

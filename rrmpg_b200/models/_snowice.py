@@ -65,43 +65,45 @@ class _SnowIceModel(BaseModel):
         return _fit.minimise(loss, self._bounds(), args)
 
 
-def _ensemble(X, args, return_storages=False, qobs=None):
+def _ensemble(X, args, return_storages=False, qobs=None, objective="mse"):
     obs, prec, mean_temp, frac, etp, frac_ice, inits, _dtype, _metric, hyst, ice = args[:11]
     return engine.snowice_gr4j(hyst, ice, prec, mean_temp, etp, frac_ice, frac, inits, _fit.as_population(X),
-                               return_storages=return_storages, qobs=qobs, want_qsim=qobs is None)
+                               return_storages=return_storages, qobs=qobs, want_qsim=qobs is None, objective=objective)
 
 
 def _loss(X, *args):
     """Loss of one trial vector (k,) or of a whole trial population (k, S).
 
-    ``loss_metric`` 'mse' is accumulated inside the kernel; 'kge' returns calc_kge itself, as the reference's
-    ``_loss`` does (``cemaneigehystgr4j.py:600-605``; its fit_Q_SCA uses 1 - KGE instead).
+    Both metrics are accumulated inside the kernel (``rrb_opts.objective``): no [T, S] discharge array is
+    materialised.  'kge' returns calc_kge itself, as the reference's ``_loss`` does
+    (``cemaneigehystgr4j.py:600-605``; its fit_Q_SCA uses 1 - KGE instead).
     """
     obs, metric = args[0], args[8]
-    if metric == "mse":
-        return _fit.finish(_ensemble(X, args, qobs=obs)['mse'], X)
-    if metric == "kge":
-        return _fit.finish(kge_columns(obs, _ensemble(X, args)['qsim']), X)
+    if metric in ("mse", "kge"):
+        return _fit.finish(_ensemble(X, args, qobs=obs, objective=metric)['mse'], X)
     raise ValueError("Invalid loss_metric. Choose 'mse' or 'kge'.")
 
 
 def _loss_Q_SCA(X, *args):
     """75 % discharge + 5 % per elevation band on the snow-covered area (``cemaneigehystgr4j.py:608-691``)."""
     obs, metric, ndsi = args[0], args[8], args[11]
-    res = _ensemble(X, args, return_storages=True)
-    qsim, sca = res['qsim'], res['sca']
+    if metric not in ("mse", "kge"):
+        raise ValueError("Invalid loss_metric. Choose 'mse' or 'kge'.")
+    # the discharge term comes out of the kernel's registers (no [T, S] qsim); the snow-covered-area terms need the
+    # per-band series, which the same launch writes as storages
+    res = engine.snowice_gr4j(args[9], args[10], args[1], args[2], args[4], args[5], args[3], args[6],
+                              _fit.as_population(X), return_storages=True, qobs=obs, want_qsim=False, objective=metric)
+    sca = res['sca']
     if sca.shape[1] < 5:
         raise IndexError("fit_Q_SCA needs five elevation bands")
     if metric == "mse":
-        loss = 0.75 * np.mean((np.asarray(obs)[:, None] - qsim) ** 2, axis=0)
+        loss = 0.75 * res['mse']
         for b in range(5):
             loss = loss + 0.05 * np.mean((np.asarray(ndsi[b])[:, None] - sca[:, b, :] * 100) ** 2, axis=0)
-    elif metric == "kge":
-        loss = 0.75 * (1 - kge_columns(obs, qsim))
+    else:
+        loss = 0.75 * (1 - res['mse'])
         for b in range(5):
             loss = loss + 0.05 * (1 - kge_columns(ndsi[b], sca[:, b, :] * 100))
-    else:
-        raise ValueError("Invalid loss_metric. Choose 'mse' or 'kge'.")
     return _fit.finish(loss, X)
 
 

@@ -15,6 +15,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device: skip them (with the reason) on a box that has none, so that a plain `pytest tests`
+    on a CPU box runs the CPU suite instead of stopping at the first GPU test.  On a GPU box nothing is skipped: a
+    library that is missing or does not load makes the tests fail loudly."""
+    if os.path.exists("/dev/nvidia0") or os.path.exists("/dev/nvidiactl"):
+        return
+    try:
+        from rrmpg_b200 import _lib
+        if _lib.device_count() > 0:
+            return
+    except Exception:
+        pass
+    skip = pytest.mark.skip(reason="no CUDA device on this box")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
         return {k: z[k] for k in z.files}
