@@ -28,7 +28,7 @@ def build_ref(force=False):
     (the GPU box: the prebuilt directory travelled with the snapshot)."""
     if not os.path.isdir(os.path.join(REF_SRC, "rrmpg")):
         return TARGET if os.path.isdir(os.path.join(TARGET, "rrmpg")) else None
-    if os.path.isdir(os.path.join(TARGET, "rrmpg")) and not force:
+    if os.path.isdir(os.path.join(TARGET, "rrmpg")) and os.path.isdir(os.path.join(TARGET, "reference_tests")) and not force:
         return TARGET
     with tempfile.TemporaryDirectory(prefix="rrmpg_ref_") as tmp:
         src = os.path.join(tmp, "src")
@@ -37,6 +37,9 @@ def build_ref(force=False):
             shutil.rmtree(TARGET)
         subprocess.check_call([sys.executable, "-m", "pip", "install", "--quiet", "--no-index", "--no-build-isolation",
                                "--no-deps", "--find-links", "/opt/wheelhouse", "--target", TARGET, src])
+        # the reference's own test-suite and its fixtures (test/test_models.py, test_tools.py, test_utils.py, test/data):
+        # tests/test_reference_suite_gpu.py runs it VERBATIM against the drop-in package (rrmpg -> rrmpg_b200)
+        shutil.copytree(os.path.join(REF_SRC, "test"), os.path.join(TARGET, "reference_tests"))
     return TARGET
 
 

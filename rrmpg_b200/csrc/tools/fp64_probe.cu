@@ -110,6 +110,64 @@ static void run_mixed(double* out, int sms, int wps) {
            NF, NI, NS, wps, ipc, ipc * NF / (NF + NI + NS), ipc * NI / (NF + NI + NS), ipc * NS / (NF + NI + NS));
 }
 
+// The same mix with THREE DISTINCT REGISTER operands per DFMA (x = fma(x, y_k, z_k), y_k / z_k per chain and per thread)
+// and two per integer instruction -- the operand pattern of real kernel code.  mixed_chain above feeds every DFMA one
+// register, one reuse-cached register and one uniform-register operand, i.e. a third of the register-file traffic.
+template <int NF, int NI>
+__global__ void mixed_chain_regs(double* out, double a, double b, int ia, int iters) {
+    double x[NF > 0 ? NF : 1], y[NF > 0 ? NF : 1], z[NF > 0 ? NF : 1];
+    int n[NI > 0 ? NI : 1], m[NI > 0 ? NI : 1];
+#pragma unroll
+    for (int k = 0; k < (NF > 0 ? NF : 1); ++k) {
+        x[k] = a + k + threadIdx.x;
+        y[k] = a + 1e-9 * (k + threadIdx.x);
+        z[k] = b * (1 + k + threadIdx.x);
+        asm volatile("" : "+d"(y[k]), "+d"(z[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < (NI > 0 ? NI : 1); ++k) {
+        n[k] = ia + k + threadIdx.x;
+        m[k] = ia * 3 + k + 7 * threadIdx.x;
+        asm volatile("" : "+r"(m[k]));
+    }
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int k = 0; k < (NF > NI ? NF : NI); ++k) {
+                if (k < NF) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x[k]) : "d"(y[k]), "d"(z[k]));
+                if (k < NI) {
+                    if ((k + r) & 1) asm volatile("xor.b32 %0, %0, %1;" : "+r"(n[k]) : "r"(m[k]));
+                    else asm volatile("add.s32 %0, %0, %1;" : "+r"(n[k]) : "r"(m[k]));
+                }
+            }
+        }
+    }
+    double acc = 0;
+#pragma unroll
+    for (int k = 0; k < (NF > 0 ? NF : 1); ++k) acc += x[k];
+#pragma unroll
+    for (int k = 0; k < (NI > 0 ? NI : 1); ++k) acc += n[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+template <int NF, int NI>
+static void run_mixed_regs(double* out, int sms, int wps) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int threads = wps * 4 * 32, iters = 1 << 14;
+    mixed_chain_regs<NF, NI><<<sms, threads>>>(out, 1.0000001, 1e-9, 3, 256);
+    cudaEventRecord(e0);
+    mixed_chain_regs<NF, NI><<<sms, threads>>>(out, 1.0000001, 1e-9, 3, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double winst = (double)sms * (threads / 32) * iters * 4.0 * (NF + NI);
+    const double ipc = winst / (ms * 1e-3) / sms / 4 / 1.965e9;
+    printf("register operands: %d DFMA + %d INT chains, %2d warps/SMSP: %.3f warp-instr/clk/SMSP (fp64 %.3f, int %.3f); "
+           "2*fp64 + int issue model predicts %.3f\n", NF, NI, wps, ipc, ipc * NF / (NF + NI), ipc * NI / (NF + NI),
+           (double)(NF + NI) / (2 * NF + NI));
+}
+
 int main() {
     double* out; long long* cyc; long long h;
     cudaMalloc(&out, sizeof(double) * 148 * 1024 * 8);
@@ -175,6 +233,14 @@ int main() {
         run_mixed<4, 0, 4>(out, sms, wps);
         run_mixed<4, 4, 4>(out, sms, wps);
         run_mixed<2, 4, 4>(out, sms, wps);
+    }
+    for (int wps : {2, 4, 8}) {
+        run_mixed_regs<4, 0>(out, sms, wps);
+        run_mixed_regs<0, 4>(out, sms, wps);
+        run_mixed_regs<4, 4>(out, sms, wps);
+        run_mixed_regs<4, 8>(out, sms, wps);
+        run_mixed_regs<2, 4>(out, sms, wps);
+        run_mixed_regs<4, 2>(out, sms, wps);
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;

@@ -98,6 +98,28 @@ def barrier():
         dist.barrier()
 
 
+_HOST_GROUP = None
+
+
+def host_group():
+    """A gloo group over all ranks (collective call: every rank must make it at the same point)."""
+    global _HOST_GROUP
+    import torch.distributed as dist
+    if _HOST_GROUP is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        _HOST_GROUP = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
+    return _HOST_GROUP
+
+
+def host_barrier():
+    """Barrier on the HOST side (gloo): the waiting ranks launch nothing on their GPUs.  An NCCL barrier parks a
+    spinning kernel on every waiting rank's device -- fatal for timing when another process (rank 0 driving all the
+    GPUs of the node through the library's own member sharding) uses those devices in the meantime."""
+    import torch.distributed as dist
+    g = host_group()
+    if g is not None:
+        dist.barrier(group=g)
+
+
 def broadcast_series(series, src=0, device=None):
     """Broadcast a dict of forcing arrays from ``src`` to every rank: ONE object broadcast of the layout
     (names and shapes, a few hundred bytes) and ONE tensor broadcast of the packed block.  Ranks other than
