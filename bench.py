@@ -43,9 +43,12 @@ REF_MEMBERS_PER_WORKER = 384  # numba reference: members per worker process and 
 # kernels of ours per device-mode step: forcing pack + FAST ensemble kernel + the PRECISE kernel queued behind it as the
 # fallback for flagged CTAs / non-finite rain, which exits at once on this workload
 LAUNCHES_PER_STEP = {"fast": 3, "precise": 2}
-# Second roofline of the HBV kernel.  Executed warp instructions per member-timestep of
-# hbv_fast2_kernel<2 members/thread, qsim only> on this forcing (ncu, profiles/r02_ncu_hbv_*), of which fp64-pipe ones:
-HBV_FAST_WARP_INSTR, HBV_FAST_FP64_INSTR = 52.6, 25.7
+# Second roofline of the HBV kernel: register-file operand delivery.  Executed warp instructions per
+# member-timestep of hbv_fast2_kernel<2 members/thread, qsim only> on this forcing (ncu, profiles/r02_ncu_full_hbv_v4_*):
+# 49.05 in total, of which 9.84 DFMA (three register operands) and 16.9 other fp64-pipe instructions (DADD / DMUL / DSETP).
+# Measured on the B200 (profiles/r02_fp64_probe_v2.txt): a DFMA with three distinct register operands issues every 3
+# cycles per SM sub-partition, one with a reuse-cached / uniform / immediate operand (and DADD / DMUL) every 2, the rest ~1.
+HBV_INSTR = {"total": 49.05, "dfma": 9.84, "fp64_other": 16.9}
 SM_COUNT, SUBPARTITIONS = 148, 4
 
 
@@ -443,22 +446,24 @@ def main():
                         "are <0.3% of it, see profiles/ launch list)"}
     issue = None
     if args.math == "fast" and members == MEMBERS_PER_GPU:
-        # what actually bounds the kernel: instruction issue under the empirical cost model
-        # cycles = 2 x fp64 + other warp instructions (fit to the wet / dry ablation runs, profiles/r02_ablations.txt;
-        # the micro-probe profiles/r02_fp64_probe.txt shows the port itself is NOT held, the mix still issues at that rate)
-        slots = 2 * HBV_FAST_FP64_INSTR + (HBV_FAST_WARP_INSTR - HBV_FAST_FP64_INSTR)
+        # what actually bounds the kernel: the rate at which a sub-partition can deliver register
+        # operands -- cycles = 3 x DFMA + 2 x other fp64 + 1 x every other warp instruction (micro-probe
+        # profiles/r02_fp64_probe_v2.txt; consistent with the wet / dry ablation runs, profiles/r02_ablations.txt)
+        other = HBV_INSTR["total"] - HBV_INSTR["dfma"] - HBV_INSTR["fp64_other"]
+        slots = 3 * HBV_INSTR["dfma"] + 2 * HBV_INSTR["fp64_other"] + other
         mhz = (clocks or {}).get("sm_mhz") or 1965.0
         ceiling = SM_COUNT * SUBPARTITIONS * mhz * 1e6 * 32 / slots
         warps = (hi - lo + 31) // 32
         per_sp = warps / (SM_COUNT * SUBPARTITIONS)
         rate = (hi - lo) * T_STEPS / (kernel_ms * 1e-3)
-        issue = {"bound": "issue, empirical cost model: 2 slots per fp64 warp instruction + 1 per other",
+        issue = {"bound": "register-operand issue: 3 cycles per DFMA with three register operands, 2 per other fp64 instruction, "
+                          "1 per other warp instruction",
                  "issue_slots_per_member_step": slots, "ceiling_member_steps_per_s": ceiling, "achieved": rate,
                  "frac": rate / ceiling, "sm_mhz_used": mhz,
                  "load_balance_limit": per_sp / float(int(per_sp) + (per_sp > int(per_sp))),
-                 "fp64_pipe_ceiling_member_steps_per_s": SM_COUNT * SUBPARTITIONS * mhz * 1e6 * 32 / (2 * HBV_FAST_FP64_INSTR),
                  "note": "second roofline, explains the HBM fraction: instruction counts from the committed ncu capture; "
-                         "load_balance_limit = mean / max member-warps per SM sub-partition for this ensemble size"}
+                         "load_balance_limit = mean / max member-warps per SM sub-partition for this ensemble size "
+                         "(65 536 members = 3.46 member-warps per sub-partition, 4 on the busiest)"}
     cpu = None
     if world == 1 and not args.no_cpu:
         cpu = cpu_baseline_run(f)

@@ -247,6 +247,34 @@ RRB_API int rrb_cemaneigegr4j_simulate_multi(const double* prec, const double* m
                                              double* G, double* eTG, double* s_store, double* r_store /* nullable x4 */,
                                              const rrb_opts* opts);
 
+/* Catchment batches of the remaining models (round 2; same conventions: every array gains a leading [C] axis, results
+ * bit-identical to C single-catchment calls).  inits, HOST memory in both modes: ABC [C] initial storages; Cemaneige
+ * [C, 2] = (snow_pack_init, thermal_state_init); the snow-ice couplings [C, 4] = (snow_pack_init, thermal_state_init,
+ * s_init, r_init) without and [C, 5] = (snow_pack_init, thermal_state_init, sca_init, s_init, r_init) with hysteresis --
+ * the argument order of the single-catchment calls.  frac_ice: [C, L]. */
+RRB_API int rrb_abc_simulate_multi(const double* prec, int64_t C, int64_t T, const double* inits, const double* params,
+                                   int64_t N, double* qsim, double* storage /* nullable */, const rrb_opts* opts);
+RRB_API int rrb_cemaneige_simulate_multi(const double* prec, const double* mean_temp, const double* frac_solid, int64_t C,
+                                         int64_t T, int64_t L, const double* inits, const double* params,
+                                         int64_t param_stride, int64_t N, double* outflow, double* G,
+                                         double* eTG /* nullable x2 */, const rrb_opts* opts);
+RRB_API int rrb_cemaneigegr4jice_simulate_multi(const double* prec, const double* mean_temp, const double* etp,
+                                                const double* frac_ice, const double* frac_solid, int64_t C, int64_t T,
+                                                int64_t L, const double* inits, const double* params, int64_t N,
+                                                double* qsim, double* G, double* eTG, double* s_store, double* r_store,
+                                                double* icemelt /* nullable x5 */, const rrb_opts* opts);
+RRB_API int rrb_cemaneigehystgr4j_simulate_multi(const double* prec, const double* mean_temp, const double* etp,
+                                                 const double* frac_solid, int64_t C, int64_t T, int64_t L,
+                                                 const double* inits, const double* params, int64_t N, double* qsim,
+                                                 double* G, double* eTG, double* s_store, double* r_store,
+                                                 double* sca /* nullable x5 */, const rrb_opts* opts);
+RRB_API int rrb_cemaneigehystgr4jice_simulate_multi(const double* prec, const double* mean_temp, const double* etp,
+                                                    const double* frac_ice, const double* frac_solid, int64_t C,
+                                                    int64_t T, int64_t L, const double* inits, const double* params,
+                                                    int64_t N, double* qsim, double* G, double* eTG, double* s_store,
+                                                    double* r_store, double* sca, double* icemelt,
+                                                    double* snowmelt /* nullable x7 */, const rrb_opts* opts);
+
 /* ---- member-independent layer preprocessing of the Cemaneige family, on the device --------
  * Replaces extrapolate_precipitation (rrmpg/models/cemaneige_utils.py:101-158), extrapolate_temperature
  * (:161-208) and calculate_solid_fraction (:16-98), i.e. the [T] -> [T, L] step of Cemaneige.simulate

@@ -72,6 +72,16 @@ _SIGS = {
                                 + [C.c_void_p] * 3 + [C.POINTER(Opts)]),
     "rrb_cemaneigegr4j_simulate_multi": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                                                       C.c_int64] + [C.c_void_p] * 5 + [C.POINTER(Opts)]),
+    "rrb_abc_simulate_multi": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_void_p, C.POINTER(Opts)]),
+    "rrb_cemaneige_simulate_multi": (C.c_int, [C.c_void_p] * 3 + [C.c_int64] * 3 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+                                     + [C.c_void_p] * 3 + [C.POINTER(Opts)]),
+    "rrb_cemaneigegr4jice_simulate_multi": (C.c_int, [C.c_void_p] * 5 + [C.c_int64] * 3 + [C.c_void_p, C.c_void_p, C.c_int64]
+                                            + [C.c_void_p] * 6 + [C.POINTER(Opts)]),
+    "rrb_cemaneigehystgr4j_simulate_multi": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] * 3 + [C.c_void_p, C.c_void_p, C.c_int64]
+                                             + [C.c_void_p] * 6 + [C.POINTER(Opts)]),
+    "rrb_cemaneigehystgr4jice_simulate_multi": (C.c_int, [C.c_void_p] * 5 + [C.c_int64] * 3 + [C.c_void_p, C.c_void_p, C.c_int64]
+                                                + [C.c_void_p] * 8 + [C.POINTER(Opts)]),
     "rrb_snow_layers": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int64] + [C.c_void_p] * 6 + [C.POINTER(Opts)]),
     "rrb_host_fast_pow": (None, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "rrb_host_fast_exp2m1": (None, [C.c_void_p, C.c_int64, C.c_void_p]),

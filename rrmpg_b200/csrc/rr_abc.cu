@@ -12,19 +12,34 @@ namespace rrb {
 
 __global__ void abc_pack_kernel(const double* __restrict__ prec, int64_t T, int64_t Tpad, double* __restrict__ F) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t < Tpad) F[t] = (t < T) ? prec[t] : 0.0;
+    const int64_t c = blockIdx.y;  // catchment
+    if (t < Tpad) F[c * Tpad + t] = (t < T) ? prec[c * T + t] : 0.0;
 }
 
-cudaError_t pack_abc(const double* prec, int64_t T, double* F, cudaStream_t s) {
+cudaError_t pack_abc(const double* prec, int64_t T, double* F, cudaStream_t s, int count) {
     int64_t Tpad = padded_steps(T, kAbcTT);
-    abc_pack_kernel<<<(unsigned)((Tpad + 255) / 256), 256, 0, s>>>(prec, T, Tpad, F);
+    abc_pack_kernel<<<dim3((unsigned)((Tpad + 255) / 256), (unsigned)count), 256, 0, s>>>(prec, T, Tpad, F);
     return cudaGetLastError();
 }
+
+// blockIdx.y = catchment of a batch (rrb_abc_simulate_multi): shift every per-catchment pointer
+#define ABC_BATCH_PROLOGUE                                                            \
+    if (batch.count > 1) {                                                            \
+        const int64_t c = blockIdx.y;                                                 \
+        F += c * batch.forcing_stride;                                                \
+        params += c * N * 3;                                                          \
+        if (qsim) qsim += c * batch.out_stride;                                       \
+        if (storage) storage += c * batch.out_stride;                                 \
+        if (obj.qobs) { obj.qobs += c * obj.T; obj.mse += c * N; }                    \
+        if (obj.obs_stats) { obj.obs_mean = obj.obs_stats[2 * c]; obj.obs_std = obj.obs_stats[2 * c + 1]; } \
+    }                                                                                 \
+    if (batch.inits) s0 = batch.inits[4 * (batch.count > 1 ? (int64_t)blockIdx.y : 0)];
 
 template <bool STORAGE, bool OBJ>
 __global__ void abc_kernel(const double* __restrict__ F, double s0, const double* __restrict__ params, int64_t N,
                            double* __restrict__ qsim, double* __restrict__ storage, Slab slab,
-                           Objective obj) {
+                           Objective obj, Batch batch) {
+    ABC_BATCH_PROLOGUE
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool active = gi < N;
     const int64_t i = active ? gi : N - 1;
@@ -77,7 +92,12 @@ __device__ __forceinline__ void st_stream_v2(double* p, double x, double y) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory");
 }
 __global__ void abc_pair_kernel(const double* __restrict__ F, double s0, const double* __restrict__ params, int64_t N,
-                                double* __restrict__ qsim, Slab slab) {
+                                double* __restrict__ qsim, Slab slab, Batch batch) {
+    {
+        double* storage = nullptr;
+        Objective obj{nullptr, nullptr, 0, 0, 0.0, 1.0, nullptr};
+        ABC_BATCH_PROLOGUE
+    }
     const int64_t pairs = N / 2;
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t i = 2 * (gi < pairs ? gi : pairs - 1);  // surplus threads recompute the last pair
@@ -115,21 +135,22 @@ __global__ void abc_pair_kernel(const double* __restrict__ F, double s0, const d
 int state_slots_abc() { return 1 + kObjSlots; }
 
 cudaError_t launch_abc(const double* F, int64_t T, double s0, const double* params, int64_t N, double* qsim,
-                       double* storage, const Slab& slab, const Objective& obj, const LaunchCfg& cfg) {
+                       double* storage, const Slab& slab, const Objective& obj, const LaunchCfg& cfg, const Batch& batch) {
     (void)T;
-    if (N <= 0) return cudaSuccess;
-    const int block = cfg.block > 0 ? cfg.block : pick_block(N, cfg.sm_count, 256);
-    const unsigned grid = (unsigned)((N + block - 1) / block);
+    if (N <= 0 || batch.count <= 0) return cudaSuccess;
+    const int block = cfg.block > 0 ? cfg.block : pick_block(N * batch.count, cfg.sm_count, 256);
+    const dim3 grid((unsigned)((N + block - 1) / block), (unsigned)batch.count);
     const size_t smem = forcing_smem_bytes<kAbcR, kAbcTT>();
     const bool st = storage != nullptr, ob = obj.qobs != nullptr;
     if (qsim && !st && !ob && (N % 2) == 0 && (reinterpret_cast<uintptr_t>(qsim) % 16) == 0) {
         const int64_t pairs = N / 2;
-        const int pblock = cfg.block > 0 ? cfg.block : pick_block(pairs, cfg.sm_count, 128);
-        abc_pair_kernel<<<(unsigned)((pairs + pblock - 1) / pblock), pblock, smem, cfg.stream>>>(F, s0, params, N, qsim, slab);
+        const int pblock = cfg.block > 0 ? cfg.block : pick_block(pairs * batch.count, cfg.sm_count, 128);
+        abc_pair_kernel<<<dim3((unsigned)((pairs + pblock - 1) / pblock), (unsigned)batch.count), pblock, smem, cfg.stream>>>(
+            F, s0, params, N, qsim, slab, batch);
         return cudaGetLastError();
     }
 #define RRB_ABC(S_, O_) \
-    abc_kernel<S_, O_><<<grid, block, smem, cfg.stream>>>(F, s0, params, N, qsim, storage, slab, obj)
+    abc_kernel<S_, O_><<<grid, block, smem, cfg.stream>>>(F, s0, params, N, qsim, storage, slab, obj, batch)
     if (st && ob) RRB_ABC(true, true);
     else if (st) RRB_ABC(true, false);
     else if (ob) RRB_ABC(false, true);

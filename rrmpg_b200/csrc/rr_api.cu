@@ -597,12 +597,13 @@ static int stage_obs_stats(Prepared& P, int64_t C) {
 
 // shared staging of a catchment batch: parameters [C][N][pwidth], per-catchment inits [C][4] (host memory in both
 // modes), observations [C][T] and the per-member objective [C][N]
-static int stage_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const double* inits4, const double** d_inits) {
+static int stage_multi(Prepared& P, int64_t C, int64_t T, int64_t N, const double* inits4, const double** d_inits,
+                       int width = 4) {
     Ctx& c = *P.c;
     int rc;
     void* di = nullptr;
-    if ((rc = c.ensure(B_SCALAR, sizeof(double) * 4 * (size_t)C, &di))) return rc;
-    RRB_CUDA(cudaMemcpyAsync(di, inits4, sizeof(double) * 4 * (size_t)C, cudaMemcpyHostToDevice, P.s));
+    if ((rc = c.ensure(B_SCALAR, sizeof(double) * (size_t)width * (size_t)C, &di))) return rc;
+    RRB_CUDA(cudaMemcpyAsync(di, inits4, sizeof(double) * (size_t)width * (size_t)C, cudaMemcpyHostToDevice, P.s));
     *d_inits = (const double*)di;
     if (P.o.qobs) {
         if ((rc = stage_in(c, P.o, B_QOBS, P.o.qobs, (size_t)(C * T), &P.d_qobs))) return rc;
@@ -1305,6 +1306,178 @@ int rrb_cemaneigegr4j_simulate_multi(const double* prec, const double* mean_temp
                                     zero4, dp + c0 * N * 6, N, x4_max, out[0], out[1], out[2], out[3], out[4], slab, ob,
                                     cfg, b);
     });
+}
+
+
+// ---- catchment batches of ABC, Cemaneige and the snow-ice couplings (completed in round 2)
+int rrb_abc_simulate_multi(const double* prec, int64_t C, int64_t T, const double* inits, const double* params, int64_t N,
+                           double* qsim, double* storage, const rrb_opts* opts) {
+    Prepared P;
+    int rc = prepare(opts, T, N, params, 3, &P);
+    if (rc) return rc;
+    if (C < 0) return fail(RRB_EINVAL, "C = %lld", (long long)C);
+    if (!prec || !inits) return fail(RRB_EINVAL, "NULL forcing / inits pointer");
+    if (!qsim && !P.o.qobs && !storage) return fail(RRB_EINVAL, "nothing to compute");
+    if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
+    if (P.o.state_in || P.o.state_out) return fail(RRB_EUNSUPPORTED, "state_in / state_out: single-catchment calls only");
+    if (N == 0 || C == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain(P);
+    const double *d_prec, *d_inits;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(C * T), &d_prec))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_PARAMS, params, (size_t)(C * N * 3), &P.d_params))) return rc;
+    std::vector<double> in4((size_t)C * 4, 0.0);
+    for (int64_t k = 0; k < C; ++k) in4[4 * k] = inits[k];
+    if ((rc = stage_multi(P, C, T, N, in4.data(), &d_inits))) return rc;
+    RRB_CUDA(cudaStreamSynchronize(P.s));  // in4 is a temporary
+    const int64_t Tpad = padded_steps(T, kAbcTT);
+    void* F = nullptr;
+    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)(C * Tpad) * kAbcR, &F))) return rc;
+    RRB_CUDA(pack_abc(d_prec, T, (double*)F, P.s, (int)C));
+    const double* dp = P.d_params;
+    const std::vector<MultiOut> outs = {{qsim, T * N}, {storage, T * N}};
+    return run_multi(P, C, T, N, outs, [=](int64_t c0, int64_t c1, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
+        Batch b{(int)(c1 - c0), Tpad * kAbcR, T * N, d_inits + 4 * c0};
+        Slab slab{0, T, 0, nullptr, 0, 0};
+        return launch_abc((const double*)F + c0 * Tpad * kAbcR, T, 0.0, dp + c0 * N * 3, N, out[0], out[1], slab, ob, cfg, b);
+    });
+}
+
+int rrb_cemaneige_simulate_multi(const double* prec, const double* mean_temp, const double* frac_solid, int64_t C, int64_t T,
+                                 int64_t L, const double* inits, const double* params, int64_t param_stride, int64_t N,
+                                 double* outflow, double* G, double* eTG, const rrb_opts* opts) {
+    Prepared P;
+    int rc = prepare(opts, T, N, params, param_stride, &P);
+    if (rc) return rc;
+    if (C < 0) return fail(RRB_EINVAL, "C = %lld", (long long)C);
+    if (!prec || !mean_temp || !frac_solid || !inits) return fail(RRB_EINVAL, "NULL forcing / inits pointer");
+    if (L < 1) return fail(RRB_EINVAL, "L = %lld", (long long)L);
+    if (L > RRB_MAX_LAYERS) return fail(RRB_EUNSUPPORTED, "L = %lld elevation layers (max %d)", (long long)L, RRB_MAX_LAYERS);
+    if (param_stride < 2) return fail(RRB_EINVAL, "param_stride = %lld (< 2)", (long long)param_stride);
+    if ((G != nullptr) != (eTG != nullptr)) return fail(RRB_EINVAL, "pass both storage outputs or none");
+    if (!outflow && !P.o.qobs && !G) return fail(RRB_EINVAL, "nothing to compute");
+    if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
+    if (P.o.state_in || P.o.state_out) return fail(RRB_EUNSUPPORTED, "state_in / state_out: ABC, HBV-Edu, GR4J single-catchment calls only");
+    if (N == 0 || C == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain(P);
+    const double *d_prec, *d_mt, *d_fr, *d_inits;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(C * T * L), &d_prec))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(C * T * L), &d_mt))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW2, frac_solid, (size_t)(C * T * L), &d_fr))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_PARAMS, params, (size_t)(C * N * param_stride), &P.d_params))) return rc;
+    std::vector<double> in4((size_t)C * 4, 0.0);
+    for (int64_t k = 0; k < C; ++k) { in4[4 * k] = inits[2 * k]; in4[4 * k + 1] = inits[2 * k + 1]; }
+    if ((rc = stage_multi(P, C, T, N, in4.data(), &d_inits))) return rc;
+    RRB_CUDA(cudaStreamSynchronize(P.s));  // in4 is a temporary
+    const int LC = cema_layer_class((int)L);
+    const int64_t fstride = forcing_stride_flagged(T, cema_TT(LC), cema_R(LC));
+    void *F = nullptr, *gt = nullptr;
+    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)(C * fstride), &F))) return rc;
+    if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers * (size_t)C, &gt))) return rc;
+    RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, nullptr, T, (int)L, (double*)F, (double*)gt, P.s, (int)C));
+    const double* dp = P.d_params;
+    const std::vector<MultiOut> outs = {{outflow, T * N}, {G, T * L * N}, {eTG, T * L * N}};
+    return run_multi(P, C, T, N, outs, [=](int64_t c0, int64_t c1, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
+        Batch b{(int)(c1 - c0), fstride, T * N, d_inits + 4 * c0};
+        Slab slab{0, T, 0, nullptr, 0, 0};
+        return launch_cemaneige((const double*)F + c0 * fstride, (const double*)gt + c0 * 2 * kCemaMaxLayers, T, (int)L, 0.0, 0.0,
+                                dp + c0 * N * param_stride, param_stride, N, out[0], out[1], out[2], slab, ob, cfg, b);
+    });
+}
+
+static int snowice_simulate_multi(int family, const double* prec, const double* mean_temp, const double* etp,
+                                  const double* frac_ice, const double* frac_solid, int64_t C, int64_t T, int64_t L,
+                                  const double* inits, const double* params, int64_t N, const SnowIceOut& o,
+                                  int n_storage_given, int n_storage_expected, const rrb_opts* opts) {
+    const bool hyst = family & 1, ice = family & 2;
+    const int k = 6 + (hyst ? 2 : 0) + (ice ? 1 : 0);
+    Prepared P;
+    int rc = prepare(opts, T, N, params, k, &P);
+    if (rc) return rc;
+    if (C < 0) return fail(RRB_EINVAL, "C = %lld", (long long)C);
+    if (!prec || !mean_temp || !etp || !frac_solid || !inits || (ice && !frac_ice))
+        return fail(RRB_EINVAL, "NULL forcing / inits pointer");
+    if (L < 1) return fail(RRB_EINVAL, "L = %lld", (long long)L);
+    if (L > RRB_MAX_LAYERS) return fail(RRB_EUNSUPPORTED, "L = %lld elevation layers (max %d)", (long long)L, RRB_MAX_LAYERS);
+    if (n_storage_given != 0 && n_storage_given != n_storage_expected)
+        return fail(RRB_EINVAL, "pass all %d storage outputs of the model or none", n_storage_expected);
+    if (!o.qsim && !P.o.qobs && n_storage_given == 0) return fail(RRB_EINVAL, "nothing to compute");
+    if (C > 65535) return fail(RRB_EUNSUPPORTED, "C = %lld catchments per call (max 65535)", (long long)C);
+    if (P.o.state_in || P.o.state_out) return fail(RRB_EUNSUPPORTED, "state_in / state_out: ABC, HBV-Edu, GR4J single-catchment calls only");
+    if (N == 0 || C == 0) return RRB_OK;
+    std::lock_guard<std::mutex> lk(P.c->mu);
+    HostDrain drain(P);
+    const double *d_prec, *d_mt, *d_fr, *d_etp, *d_fice = nullptr, *d_inits;
+    if ((rc = stage_in(*P.c, P.o, B_RAW0, prec, (size_t)(C * T * L), &d_prec))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW1, mean_temp, (size_t)(C * T * L), &d_mt))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW2, frac_solid, (size_t)(C * T * L), &d_fr))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_RAW3, etp, (size_t)(C * T), &d_etp))) return rc;
+    if (ice && (rc = stage_in(*P.c, P.o, B_RAW4, frac_ice, (size_t)(C * L), &d_fice))) return rc;
+    if ((rc = stage_in(*P.c, P.o, B_PARAMS, params, (size_t)(C * N * k), &P.d_params))) return rc;
+    double x4_max;  // (uses the scalar scratch slot: before the inits are staged into it)
+    if ((rc = resolve_x4_max(&P, params, C * N, k, (hyst ? 4 : 2) + 3, &x4_max))) return rc;
+    if (!(x4_max <= RRB_MAX_X4))
+        return fail(RRB_EUNSUPPORTED, "GR4J x4 up to %g in this batch; the unit hydrograph buffers support x4 <= %g",
+                    x4_max, RRB_MAX_X4);
+    // rows of kSnowIceInitsStride: (snow_pack_init, thermal_state_init, s_init, r_init, sca_init, -, -, -)
+    const int nin = hyst ? 5 : 4;
+    std::vector<double> in8((size_t)C * kSnowIceInitsStride, 0.0);
+    for (int64_t c = 0; c < C; ++c) {
+        const double* r = inits + c * nin;
+        double* w = in8.data() + c * kSnowIceInitsStride;
+        w[0] = r[0]; w[1] = r[1];
+        if (hyst) { w[4] = r[2]; w[2] = r[3]; w[3] = r[4]; }
+        else { w[2] = r[2]; w[3] = r[3]; }
+    }
+    if ((rc = stage_multi(P, C, T, N, in8.data(), &d_inits, kSnowIceInitsStride))) return rc;
+    RRB_CUDA(cudaStreamSynchronize(P.s));  // in8 is a temporary
+    const int LC = cema_layer_class((int)L);
+    const int64_t fstride = forcing_stride_flagged(T, cema_TT(LC), cema_R(LC));
+    void *F = nullptr, *gt = nullptr;
+    if ((rc = P.c->ensure(B_F, sizeof(double) * (size_t)(C * fstride), &F))) return rc;
+    if ((rc = P.c->ensure(B_GT, sizeof(double) * 2 * kCemaMaxLayers * (size_t)C, &gt))) return rc;
+    RRB_CUDA(pack_cemaneige(d_prec, d_mt, d_fr, d_etp, T, (int)L, (double*)F, (double*)gt, P.s, (int)C));
+    const double* dp = P.d_params;
+    const std::vector<MultiOut> outs = {{o.qsim, T * N}, {o.G, T * L * N}, {o.eTG, T * L * N}, {o.s_store, T * N},
+                                        {o.r_store, T * N}, {o.sca, T * L * N}, {o.icemelt, T * N}, {o.snowmelt, T * N}};
+    const double zero5[5] = {0, 0, 0, 0, 0};
+    return run_multi(P, C, T, N, outs, [=](int64_t c0, int64_t c1, double* const* out, const Objective& ob, const LaunchCfg& cfg) {
+        Batch b{(int)(c1 - c0), fstride, T * N, d_inits + kSnowIceInitsStride * c0};
+        Slab slab{0, T, 0, nullptr, 0, 0};
+        SnowIceOut so{out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]};
+        return launch_snowice(family, (const double*)F + c0 * fstride, (const double*)gt + c0 * 2 * kCemaMaxLayers,
+                              d_fice ? d_fice + c0 * L : nullptr, T, (int)L, zero5, dp + c0 * N * k, N, x4_max, so, slab, ob, cfg, b);
+    });
+}
+
+int rrb_cemaneigegr4jice_simulate_multi(const double* prec, const double* mean_temp, const double* etp, const double* frac_ice,
+                                        const double* frac_solid, int64_t C, int64_t T, int64_t L, const double* inits,
+                                        const double* params, int64_t N, double* qsim, double* G, double* eTG,
+                                        double* s_store, double* r_store, double* icemelt, const rrb_opts* opts) {
+    SnowIceOut o{qsim, G, eTG, s_store, r_store, nullptr, icemelt, nullptr};
+    const int n = (G != nullptr) + (eTG != nullptr) + (s_store != nullptr) + (r_store != nullptr) + (icemelt != nullptr);
+    return snowice_simulate_multi(2, prec, mean_temp, etp, frac_ice, frac_solid, C, T, L, inits, params, N, o, n, 5, opts);
+}
+
+int rrb_cemaneigehystgr4j_simulate_multi(const double* prec, const double* mean_temp, const double* etp,
+                                         const double* frac_solid, int64_t C, int64_t T, int64_t L, const double* inits,
+                                         const double* params, int64_t N, double* qsim, double* G, double* eTG,
+                                         double* s_store, double* r_store, double* sca, const rrb_opts* opts) {
+    SnowIceOut o{qsim, G, eTG, s_store, r_store, sca, nullptr, nullptr};
+    const int n = (G != nullptr) + (eTG != nullptr) + (s_store != nullptr) + (r_store != nullptr) + (sca != nullptr);
+    return snowice_simulate_multi(1, prec, mean_temp, etp, nullptr, frac_solid, C, T, L, inits, params, N, o, n, 5, opts);
+}
+
+int rrb_cemaneigehystgr4jice_simulate_multi(const double* prec, const double* mean_temp, const double* etp,
+                                            const double* frac_ice, const double* frac_solid, int64_t C, int64_t T, int64_t L,
+                                            const double* inits, const double* params, int64_t N, double* qsim, double* G,
+                                            double* eTG, double* s_store, double* r_store, double* sca, double* icemelt,
+                                            double* snowmelt, const rrb_opts* opts) {
+    SnowIceOut o{qsim, G, eTG, s_store, r_store, sca, icemelt, snowmelt};
+    const int n = (G != nullptr) + (eTG != nullptr) + (s_store != nullptr) + (r_store != nullptr) + (sca != nullptr) +
+                  (icemelt != nullptr) + (snowmelt != nullptr);
+    return snowice_simulate_multi(3, prec, mean_temp, etp, frac_ice, frac_solid, C, T, L, inits, params, N, o, n, 7, opts);
 }
 
 // ---- Cemaneige-family layer preprocessing ----

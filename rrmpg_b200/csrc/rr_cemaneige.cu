@@ -155,11 +155,12 @@ int state_slots_cemaneigegr4j(int L, double x4_max) {
 
 cudaError_t launch_cemaneige(const double* F, const double* g_tresh, int64_t T, int L, double g0, double e0,
                              const double* params, int64_t pstride, int64_t N, double* outflow, double* G,
-                             double* eTG, const Slab& slab, const Objective& obj, const LaunchCfg& cfg) {
-    if (N <= 0) return cudaSuccess;
+                             double* eTG, const Slab& slab, const Objective& obj, const LaunchCfg& cfg, const Batch& batch) {
+    if (N <= 0 || batch.count <= 0) return cudaSuccess;
     if (L < 1 || L > kCemaMaxLayers) return cudaErrorInvalidValue;
     CemaArgs a{F, g_tresh, L, T, g0, e0, 0.0, 0.0, 0.0, params, pstride, N, nullptr,
-               forcing_flag(F, T, cema_TT(layer_class(L)), cema_R(layer_class(L))), 1, 0, nullptr};
+               forcing_flag(F, T, cema_TT(layer_class(L)), cema_R(layer_class(L))), batch.count, batch.forcing_stride,
+               batch.inits, 4};
     CemaOut out{outflow, G, eTG, nullptr, nullptr, nullptr, nullptr, nullptr};
     switch (layer_class(L)) {
         case 1: return cema_launch_variant<1, NoGr4j, false, 0>(a, out, slab, obj, cfg);
@@ -174,7 +175,7 @@ cudaError_t launch_cemaneigegr4j(const double* F, const double* g_tresh, int64_t
                                  const Objective& obj, const LaunchCfg& cfg, const Batch& batch) {
     CemaArgs a{F, g_tresh, L, T, inits4[0], inits4[1], 0.0, inits4[2], inits4[3], params, 6, N, nullptr,
                forcing_flag(F, T, cema_TT(layer_class(L)), cema_R(layer_class(L))), batch.count, batch.forcing_stride,
-               batch.inits};
+               batch.inits, 4};
     CemaOut out{qsim, G, eTG, s_store, r_store, nullptr, nullptr, nullptr};
     return cema_launch_coupled<0>(a, x4_max, out, slab, obj, cfg);
 }

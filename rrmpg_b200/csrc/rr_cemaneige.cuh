@@ -44,7 +44,8 @@ struct CemaArgs {
     // catchment batch (blockIdx.y = catchment): count = 1 and zero strides for the ordinary call
     int count;
     int64_t forcing_stride;  // doubles between the packed forcing blocks (flag slot included)
-    const double* inits_c;   // device [count][4] = (snow_pack_init, thermal_state_init, s_init, r_init), nullable
+    const double* inits_c;   // device [count][inits_stride] = (snow_pack_init, thermal_state_init, s_init, r_init[, sca_init]), nullable
+    int inits_stride;        // 4, or kSnowIceInitsStride for the snow-ice batches (column 4 = sca_init)
 };
 
 template <int LC>
@@ -93,10 +94,12 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
     const uint32_t* __restrict__ fflag =
         reinterpret_cast<const uint32_t*>(reinterpret_cast<const double*>(a.fflag) + cb * a.forcing_stride);
     const double* __restrict__ g_tresh = a.g_tresh + cb * 2 * kCemaMaxLayers;
-    double g0 = a.g0, e0 = a.e0, s_init = a.s_init, r_init = a.r_init;
+    double g0 = a.g0, e0 = a.e0, s_init = a.s_init, r_init = a.r_init, sca0 = a.sca0;
     if (a.inits_c) {
-        g0 = a.inits_c[4 * cb]; e0 = a.inits_c[4 * cb + 1];
-        s_init = a.inits_c[4 * cb + 2]; r_init = a.inits_c[4 * cb + 3];
+        const double* ic_ = a.inits_c + (int64_t)a.inits_stride * cb;
+        g0 = ic_[0]; e0 = ic_[1];
+        s_init = ic_[2]; r_init = ic_[3];
+        if (a.inits_stride > 4) sca0 = ic_[4];
     }
     const int64_t N = a.N;
     int L = a.L;
@@ -121,11 +124,11 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
         eTG[l] = 0.0;
         if (HYST) {
             // sca[t-1] at t = 0 is sca[T-1], still 0 from np.zeros -- or sca_init itself when T == 1 (:126)
-            sca_prev[l] = (a.T == 1) ? a.sca0 : 0.0;
+            sca_prev[l] = (a.T == 1) ? sca0 : 0.0;
             swe_max[l] = 0.0;
             thmelt[l] = ((l < L) ? g_tresh[kCemaMaxLayers + l] : 0.0) * Rsp;  // Psolannual * Rsp, :139
         }
-        if (ICE) fice[l] = (l < L) ? a.frac_ice[l] : 0.0;
+        if (ICE) fice[l] = (l < L) ? a.frac_ice[cb * a.L + l] : 0.0;
     }
     double inv_thacc = 1.0 / Thacc;
     const uint32_t thacc_span = HYST ? div_invariant_span(Thacc) : 0u;
@@ -219,7 +222,7 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
         // (hysteresis: Thacc == 0 -- the lower default bound, reachable by the polish step of fit() -- makes
         // snow_balance / Thacc a NaN that the reference's max(0, NaN) = 0 absorbs; step_fast has no special-value
         // handling, so such CTAs take the reference-order step: thacc_span != 0 <=> Thacc in [2^-60, 2^60])
-        bool sane = gr.sane && *fflag == 0u && fabs(g0) <= 1e6 && fabs(e0) <= 1e6 && fabs(a.sca0) <= 1e6 &&
+        bool sane = gr.sane && *fflag == 0u && fabs(g0) <= 1e6 && fabs(e0) <= 1e6 && fabs(sca0) <= 1e6 &&
                     (HYST ? thacc_span != 0u : snow_ok);
         for (int k = 0; k < (int)a.pstride; ++k) sane = sane && fabs(p[k]) <= 1e6;
         if (ICE) {

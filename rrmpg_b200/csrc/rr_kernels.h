@@ -92,7 +92,8 @@ inline int64_t forcing_stride_flagged(int64_t T, int TT, int R) {
 }
 
 // ---- forcing packers (device pointers in, packed F[Tpad][R] out) ----
-cudaError_t pack_abc(const double* prec, int64_t T, double* F, cudaStream_t s);
+// count catchments: prec [count][T]; F [count][Tpad]
+cudaError_t pack_abc(const double* prec, int64_t T, double* F, cudaStream_t s, int count = 1);
 // count catchments: inputs are [count][T] (PE_m, T_m: [count][12]), F is [count][Tpad][R] followed by the flag word
 // (non-zero: a precipitation value is not finite -- the FAST kernel then leaves the launch to the PRECISE one)
 cudaError_t pack_hbvedu(const double* temp, const double* prec, const int8_t* month0, const double* PE_m,
@@ -117,8 +118,10 @@ cudaError_t launch_snow_layers(const double* prec, const double* mean_temp, cons
                                double* layer_mean, double* frac_solid, cudaStream_t s);
 
 // ---- model launches ----
+// batch.inits (nullable): device [count][4], column 0 = initial storage of the catchment
 cudaError_t launch_abc(const double* F, int64_t T, double s0, const double* params, int64_t N, double* qsim,
-                       double* storage, const Slab& slab, const Objective& obj, const LaunchCfg& cfg);
+                       double* storage, const Slab& slab, const Objective& obj, const LaunchCfg& cfg,
+                       const Batch& batch = Batch{1, 0, 0, nullptr});
 
 cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, const double* params, int64_t N,
                           double* qsim, double* snow, double* soil, double* s1, double* s2, const Slab& slab,
@@ -131,9 +134,11 @@ cudaError_t launch_gr4j(const double* F, int64_t T, double s_init, double r_init
                         const Slab& slab, const Objective& obj, const LaunchCfg& cfg,
                         const Batch& batch = Batch{1, 0, 0, nullptr});
 
+// batch.inits (nullable): device [count][4] = (snow_pack_init, thermal_state_init, -, -)
 cudaError_t launch_cemaneige(const double* F, const double* g_tresh, int64_t T, int L, double g0, double e0,
                              const double* params, int64_t pstride, int64_t N, double* outflow, double* G,
-                             double* eTG, const Slab& slab, const Objective& obj, const LaunchCfg& cfg);
+                             double* eTG, const Slab& slab, const Objective& obj, const LaunchCfg& cfg,
+                             const Batch& batch = Batch{1, 0, 0, nullptr});
 
 cudaError_t launch_cemaneigegr4j(const double* F, const double* g_tresh, int64_t T, int L, const double* inits4,
                                  const double* params, int64_t N, double x4_max, double* qsim, double* G,
@@ -146,9 +151,13 @@ cudaError_t launch_cemaneigegr4j(const double* F, const double* g_tresh, int64_t
 struct SnowIceOut {
     double *qsim, *G, *eTG, *s_store, *r_store, *sca, *icemelt, *snowmelt;
 };
+// batch: frac_ice [count][L]; batch.inits (nullable): device [count][8] rows = (snow_pack_init, thermal_state_init, s_init,
+// r_init, sca_init, -, -, -) -- the only launch whose inits rows are 8 wide (SnowIceBatch::kInitsStride)
+constexpr int kSnowIceInitsStride = 8;
 cudaError_t launch_snowice(int family, const double* F, const double* g_tresh, const double* frac_ice, int64_t T, int L,
                            const double* inits5, const double* params, int64_t N, double x4_max, const SnowIceOut& o,
-                           const Slab& slab, const Objective& obj, const LaunchCfg& cfg);
+                           const Slab& slab, const Objective& obj, const LaunchCfg& cfg,
+                           const Batch& batch = Batch{1, 0, 0, nullptr});
 int state_slots_snowice(int family, int L, double x4_max);
 
 // number of carry slots a model needs in Slab::state

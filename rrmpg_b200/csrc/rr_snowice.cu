@@ -18,10 +18,11 @@ int state_slots_snowice(int family, int L, double x4_max) {
 
 cudaError_t launch_snowice(int family, const double* F, const double* g_tresh, const double* frac_ice, int64_t T, int L,
                            const double* inits5, const double* params, int64_t N, double x4_max, const SnowIceOut& o,
-                           const Slab& slab, const Objective& obj, const LaunchCfg& cfg) {
+                           const Slab& slab, const Objective& obj, const LaunchCfg& cfg, const Batch& batch) {
     const int k = 6 + ((family & 1) ? 2 : 0) + ((family & 2) ? 1 : 0);
     CemaArgs a{F, g_tresh, L, T, inits5[0], inits5[1], inits5[2], inits5[3], inits5[4], params, k, N, frac_ice,
-               forcing_flag(F, T, cema_TT(cema_layer_class(L)), cema_R(cema_layer_class(L))), 1, 0, nullptr};
+               forcing_flag(F, T, cema_TT(cema_layer_class(L)), cema_R(cema_layer_class(L))), batch.count,
+               batch.forcing_stride, batch.inits, kSnowIceInitsStride};
     CemaOut out{o.qsim, o.G, o.eTG, o.s_store, o.r_store, o.sca, o.icemelt, o.snowmelt};
     switch (family) {
         case 1: return launch_snowice_f1(a, x4_max, out, slab, obj, cfg);

@@ -142,7 +142,7 @@ class _Call:
                 self._obs_stats(qobs)
         if not self.torch_mode:
             self._devices(devices)
-        elif devices is not None:
+        elif devices not in (None, "one"):
             raise ValueError("devices= needs host (numpy) arrays: device tensors live on one GPU")
 
     def _obs_stats(self, qobs):
@@ -615,6 +615,113 @@ def cemaneigegr4j_multi(prec, mean_temp, etp, frac_solid, inits, params, return_
             _lib.ptr(prec), _lib.ptr(mean_temp), _lib.ptr(etp), _lib.ptr(frac_solid), Cc, T, L, _lib.ptr(ini), _lib.ptr(P),
             N, _lib.ptr(q), _lib.ptr(G), _lib.ptr(E), _lib.ptr(s), _lib.ptr(r), C.byref(c.opts)))
     return _result(c, ["qsim", "G", "eTG", "s_store", "r_store"], [q, G, E, s, r])
+
+
+def abc_multi(prec, inits, params, return_storage=False, qobs=None, want_qsim=True, math=DEFAULT_MATH, device=None,
+              block=0, out=None, objective="mse"):
+    """ABC model for C independent catchments with N members each, one launch.
+
+    prec: [C, T]; inits: scalar or [C] initial storages; params: [C, N, 3] (or a [C, N] record array); qobs: [C, T].
+    Returns {'qsim': [C, T, N], 'storage', 'mse': [C, N]}; bit-identical to looping ``abc`` over the catchments."""
+    params = _records_to_matrix(params)
+    c = _Call([prec, params], math, device, block, 0, None, objective=objective, devices="one", fusable=False)
+    prec = c.f64(prec)
+    if prec.ndim != 2:
+        raise ValueError("expected prec [C, T]")
+    Cc, T = prec.shape
+    P, N = _multi_common(c, params, 3, qobs, Cc, T)
+    ini = np.ascontiguousarray(np.broadcast_to(np.asarray(inits, dtype=np.float64).reshape(-1), (Cc,)))
+    c.keep.append(ini)
+    out = out or {}
+    q = c.empty((Cc, T, N), out.get("qsim")) if _want(want_qsim) else None
+    st = c.empty((Cc, T, N), out.get("storage")) if return_storage else None
+    if Cc > 0 and T > 0 and N > 0:
+        _lib.check(_lib.lib().rrb_abc_simulate_multi(_lib.ptr(prec), Cc, T, _lib.ptr(ini), _lib.ptr(P), N, _lib.ptr(q),
+                                                     _lib.ptr(st), C.byref(c.opts)))
+    return _result(c, ["qsim", "storage"], [q, st])
+
+
+def cemaneige_multi(prec, mean_temp, frac_solid, inits, params, return_storages=False, qobs=None, want_outflow=True,
+                    math=DEFAULT_MATH, device=None, block=0, out=None, objective="mse"):
+    """Cemaneige snow routine for C independent catchments with N members each, one launch.
+
+    prec, mean_temp, frac_solid: [C, T, L]; inits: (2,) or [C, 2] = (snow_pack_init, thermal_state_init);
+    params: [C, N, k >= 2] whose first two fields are (CTG, Kf).  Returns {'outflow': [C, T, N], 'G', 'eTG':
+    [C, T, L, N], 'mse': [C, N]}; bit-identical to looping ``cemaneige`` over the catchments."""
+    params = _records_to_matrix(params)
+    c = _Call([prec, mean_temp, frac_solid, params], math, device, block, 0, None, objective=objective, devices="one",
+              fusable=False)
+    prec = c.f64(prec); mean_temp = c.f64(mean_temp, prec.shape); frac_solid = c.f64(frac_solid, prec.shape)
+    if prec.ndim != 3:
+        raise ValueError("layer arrays must be [C, T, L]")
+    Cc, T, L = prec.shape
+    width = int(params.shape[2]) if np.ndim(params) == 3 else 2
+    if width < 2:
+        raise ValueError("Cemaneige parameter records start with (CTG, Kf)")
+    P, N = _multi_common(c, params, width, qobs, Cc, T)
+    ini = np.ascontiguousarray(np.broadcast_to(np.asarray(inits, dtype=np.float64).reshape(-1, 2), (Cc, 2)))
+    c.keep.append(ini)
+    out = out or {}
+    q = c.empty((Cc, T, N), out.get("outflow")) if _want(want_outflow) else None
+    G, E = (c.empty((Cc, T, L, N), out.get("G")), c.empty((Cc, T, L, N), out.get("eTG"))) if return_storages else (None, None)
+    if Cc > 0 and T > 0 and N > 0:
+        _lib.check(_lib.lib().rrb_cemaneige_simulate_multi(
+            _lib.ptr(prec), _lib.ptr(mean_temp), _lib.ptr(frac_solid), Cc, T, L, _lib.ptr(ini), _lib.ptr(P), width, N,
+            _lib.ptr(q), _lib.ptr(G), _lib.ptr(E), C.byref(c.opts)))
+    return _result(c, ["outflow", "G", "eTG"], [q, G, E])
+
+
+def snowice_gr4j_multi(hyst, ice, prec, mean_temp, etp, frac_ice, frac_solid, inits, params, return_storages=False,
+                       qobs=None, want_qsim=True, math=DEFAULT_MATH, device=None, block=0, out=None, x4_max=0.0,
+                       objective="mse"):
+    """The snow(+hysteresis)(+ice)+GR4J couplings for C independent catchments with N members each, one launch.
+
+    Layer arrays [C, T, L]; etp [C, T]; frac_ice [C, L] (ice models); inits (4,) / [C, 4] without and (5,) / [C, 5] with
+    hysteresis (the order of ``snowice_gr4j``); params [C, N, 7 | 8 | 9].  Bit-identical to looping ``snowice_gr4j``."""
+    if not (hyst or ice):
+        raise ValueError("use cemaneigegr4j_multi for the plain coupling")
+    k = 6 + (2 if hyst else 0) + (1 if ice else 0)
+    nin = 5 if hyst else 4
+    params = _records_to_matrix(params)
+    arrays = [prec, mean_temp, etp, frac_solid, params] + ([frac_ice] if ice else [])
+    c = _Call(arrays, math, device, block, 0, None, x4_max, objective=objective, devices="one", fusable=False)
+    prec = c.f64(prec); mean_temp = c.f64(mean_temp, prec.shape); frac_solid = c.f64(frac_solid, prec.shape)
+    if prec.ndim != 3:
+        raise ValueError("layer arrays must be [C, T, L]")
+    Cc, T, L = prec.shape
+    etp = c.f64(etp, (Cc, T))
+    fice = c.f64(frac_ice, (Cc, L)) if ice else None
+    P, N = _multi_common(c, params, k, qobs, Cc, T)
+    ini = np.ascontiguousarray(np.broadcast_to(np.asarray(inits, dtype=np.float64).reshape(-1, nin), (Cc, nin)))
+    c.keep.append(ini)
+    out = out or {}
+    e3 = lambda name: c.empty((Cc, T, N), out.get(name))
+    e4 = lambda name: c.empty((Cc, T, L, N), out.get(name))
+    q = e3("qsim") if _want(want_qsim) else None
+    G = E = s = r = sca = im = sm = None
+    if return_storages:
+        G, E, s, r = e4("G"), e4("eTG"), e3("s_store"), e3("r_store")
+        if hyst:
+            sca = e4("sca")
+        if ice:
+            im = e3("icemelt")
+        if hyst and ice:
+            sm = e3("snowmelt")
+    p_, L_ = _lib.ptr, _lib.lib()
+    if Cc > 0 and T > 0 and N > 0:
+        if hyst and ice:
+            rc = L_.rrb_cemaneigehystgr4jice_simulate_multi(p_(prec), p_(mean_temp), p_(etp), p_(fice), p_(frac_solid), Cc, T, L,
+                                                            p_(ini), p_(P), N, p_(q), p_(G), p_(E), p_(s), p_(r), p_(sca), p_(im),
+                                                            p_(sm), C.byref(c.opts))
+        elif hyst:
+            rc = L_.rrb_cemaneigehystgr4j_simulate_multi(p_(prec), p_(mean_temp), p_(etp), p_(frac_solid), Cc, T, L, p_(ini),
+                                                         p_(P), N, p_(q), p_(G), p_(E), p_(s), p_(r), p_(sca), C.byref(c.opts))
+        else:
+            rc = L_.rrb_cemaneigegr4jice_simulate_multi(p_(prec), p_(mean_temp), p_(etp), p_(fice), p_(frac_solid), Cc, T, L,
+                                                        p_(ini), p_(P), N, p_(q), p_(G), p_(E), p_(s), p_(r), p_(im),
+                                                        C.byref(c.opts))
+        _lib.check(rc)
+    return _result(c, ["qsim", "G", "eTG", "s_store", "r_store", "sca", "icemelt", "snowmelt"], [q, G, E, s, r, sca, im, sm])
 
 
 def snow_layers(prec, mean_temp, min_temp, max_temp, met_station_height, altitudes=(), device=None):

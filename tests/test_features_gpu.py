@@ -303,3 +303,74 @@ def test_sharding_argument_errors():
         engine.hbvedu(*args, devices=[0, 99])
     with pytest.raises(ValueError):
         engine.hbvedu(*args, devices=[0, 0], return_state=True)
+
+
+# ------------------------------------------------------------------ catchment batches of the remaining models
+def test_abc_cemaneige_and_snow_ice_multi_catchment_equal_a_loop_over_catchments(monkeypatch):
+    """rrb_abc / cemaneige / cemaneigegr4jice / cemaneigehystgr4j / cemaneigehystgr4jice _simulate_multi: grid.y =
+    catchment with per-catchment forcing, G_tresh, initial states (incl. sca_init) and glacier fractions -- bit-identical
+    to one call per catchment; host mode through the chunked D2H ring, device mode with the fused objective."""
+    import torch
+    from rrmpg_b200.models import _snow_inputs, Cemaneige, CemaneigeGR4JIce, CemaneigeHystGR4J, CemaneigeHystGR4JIce
+    monkeypatch.setenv("RRMPG_B200_MULTI_CHUNK_BYTES", str(3 << 20))  # several chunks through the ring
+    Cn, T, N = 3, 400, 70
+    fs = [synthetic.forcing(T, seed=700 + c) for c in range(Cn)]
+    qobs = np.abs(np.random.default_rng(6).normal(1.5, 0.5, (Cn, T))) + 0.1
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    # ---- ABC
+    prec = np.stack([f["prec"] for f in fs])
+    Pa = np.stack([engine.pack_params(synthetic.random_params(ABCModel(), N, seed=800 + c)) for c in range(Cn)])
+    s0 = np.array([0.0, 5.0, 12.5])
+    multi = engine.abc_multi(prec, s0, Pa, return_storage=True, qobs=qobs, objective="nse")
+    for c in range(Cn):
+        one = engine.abc(prec[c], s0[c], Pa[c], return_storage=True, qobs=qobs[c], objective="nse")
+        for nm in one:
+            assert_bits_equal(multi[nm][c], one[nm], f"abc catchment {c} {nm}")
+    pair = engine.abc_multi(prec, s0, Pa)["qsim"]                      # discharge only: the two-members-per-thread kernel
+    assert_bits_equal(pair, multi["qsim"], "abc_multi pair kernel")
+    r = engine.abc_multi(t(prec), s0, t(Pa), qobs=t(qobs), want_qsim=False, objective="nse")
+    assert_bits_equal(r["mse"].cpu().numpy(), multi["mse"], "abc device-mode objective")
+    # ---- layer arrays: catchments at different heights, one without precipitation (G_tresh = 0)
+    alts = [550, 620, 700, 785, 920]
+    lay = [_snow_inputs.to_layers(f["prec"] * (c != 1), f["temp"] - 2 * c, f["min_temp"] - 2 * c, f["max_temp"] - 2 * c,
+                                  400 + 60 * c, np.array(alts, dtype=float)) for c, f in enumerate(fs)]
+    lp, lt, fr = (np.stack([l[k] for l in lay]) for k in range(3))
+    etp = np.stack([f["etp"] for f in fs])
+    # ---- Cemaneige
+    Pc = np.stack([engine.pack_params(synthetic.random_params(Cemaneige(), N, seed=810 + c)) for c in range(Cn)])
+    ini2 = np.array([[0.0, 0.0], [20.0, -1.0], [3.0, 0.0]])
+    multi = engine.cemaneige_multi(lp, lt, fr, ini2, Pc, return_storages=True, qobs=qobs)
+    for c in range(Cn):
+        one = engine.cemaneige(lp[c], lt[c], fr[c], ini2[c, 0], ini2[c, 1], Pc[c], return_storages=True, qobs=qobs[c])
+        for nm in one:
+            assert_bits_equal(multi[nm][c], one[nm], f"cemaneige catchment {c} {nm}")
+    # ---- the three snow-ice couplings
+    fice = np.array([[0.1, 0.2, 0.0, 0.3, 0.05], [0.0] * 5, [0.5, 0.1, 0.1, 0.1, 0.2]])
+    for cls, hyst, ice in ((CemaneigeGR4JIce, False, True), (CemaneigeHystGR4J, True, False), (CemaneigeHystGR4JIce, True, True)):
+        Ps = np.stack([engine.pack_params(synthetic.random_params(cls(), N, seed=820 + c)) for c in range(Cn)])
+        ini = (np.array([[0, 0, 0.6, 0.7], [10, -0.5, 0.2, 0.9], [0, 0, 0.0, 0.1]], dtype=float) if not hyst else
+               np.array([[0, 0, 0.0, 0.6, 0.7], [10, -0.5, 0.4, 0.2, 0.9], [0, 0, 1.0, 0.0, 0.1]], dtype=float))
+        x4 = float(Ps[..., (4 if hyst else 2) + 3].max())
+        multi = engine.snowice_gr4j_multi(hyst, ice, lp, lt, etp, fice if ice else None, fr, ini, Ps, return_storages=True,
+                                          qobs=qobs, objective="kge", x4_max=x4)
+        for c in range(Cn):
+            one = engine.snowice_gr4j(hyst, ice, lp[c], lt[c], etp[c], fice[c] if ice else None, fr[c], ini[c], Ps[c],
+                                      return_storages=True, qobs=qobs[c], objective="kge", x4_max=x4)
+            assert set(one) == set(multi)
+            for nm in one:
+                assert_bits_equal(multi[nm][c], one[nm], f"{cls.__name__} catchment {c} {nm}")
+        r = engine.snowice_gr4j_multi(hyst, ice, t(lp), t(lt), t(etp), t(fice) if ice else None, t(fr), ini, t(Ps),
+                                      qobs=t(qobs), want_qsim=False, objective="kge", x4_max=x4)
+        assert set(r) == {"mse"}
+        assert_bits_equal(r["mse"].cpu().numpy(), multi["mse"], f"{cls.__name__} device-mode objective")
+    # one-step series: sca[t-1] at t = 0 wraps to sca[T-1] = sca_init when T == 1 (cemaneigehyst_model.py:126)
+    Ps = np.stack([engine.pack_params(synthetic.random_params(CemaneigeHystGR4J(), 8, seed=830 + c)) for c in range(Cn)])
+    ini = np.array([[5, 0, 0.3, 0.6, 0.7], [5, 0, 0.9, 0.6, 0.7], [5, 0, 0.0, 0.6, 0.7]], dtype=float)
+    m1 = engine.snowice_gr4j_multi(True, False, lp[:, :1], lt[:, :1], etp[:, :1], None, fr[:, :1], ini, Ps, return_storages=True,
+                                   x4_max=10.0)
+    for c in range(Cn):
+        o1 = engine.snowice_gr4j(True, False, lp[c, :1], lt[c, :1], etp[c, :1], None, fr[c, :1], ini[c], Ps[c],
+                                 return_storages=True, x4_max=10.0)
+        for nm in o1:
+            assert_bits_equal(m1[nm][c], o1[nm], f"T = 1, catchment {c} {nm}")

@@ -536,7 +536,7 @@ def test_snow_ice_time_slabs_and_objective():
 
 
 # ------------------------------------------------------------------ BASELINE configs 3 and 4 at (per-GPU) full size
-def test_full_size_gr4j_device_resident_properties():
+def test_full_size_gr4j_device_resident_properties(capsys):
     """BASELINE config 3 at its REAL size when the device has the room: GR4J, 1 048 576 members x 14 610 steps, the
     122.6 GB discharge array device resident (cudaMemGetInfo >= 130 GB free; otherwise 2^18 members, and the test
     prints which ran).  Size-independent properties over the whole array computed slab-wise on the device (finite,
@@ -547,8 +547,9 @@ def test_full_size_gr4j_device_resident_properties():
     dev = torch.device("cuda:0")
     free, total = torch.cuda.mem_get_info(dev)
     N = 1 << 20 if free >= 130e9 else 1 << 18
-    print(f"\n[config 3] GR4J {N} members x {T} steps ({N * T * 8 / 1e9:.1f} GB discharge array), "
-          f"{free / 1e9:.0f} of {total / 1e9:.0f} GB free on the device")
+    with capsys.disabled():  # which size ran belongs in the log of a -q run
+        print(f"\n[config 3] GR4J {N} members x {T} steps ({N * T * 8 / 1e9:.1f} GB discharge array), "
+              f"{free / 1e9:.0f} of {total / 1e9:.0f} GB free on the device")
     f = synthetic.forcing(T)
     P = engine.pack_params(synthetic.random_params(GR4J(), N))
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
