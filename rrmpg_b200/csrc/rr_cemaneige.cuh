@@ -369,7 +369,10 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
         const SnowOut w = snow_part(first_c, snow_c, f);
         route_part(fast_c, w, f[3 * LC], t);
     };
-    constexpr int GROUP = (COUPLED && LC <= 5) ? 2 : 1;
+#ifndef RRB_CEMA_GROUP
+#define RRB_CEMA_GROUP 2
+#endif
+    constexpr int GROUP = (COUPLED && LC <= 5) ? RRB_CEMA_GROUP : 1;
 
     auto run = [&](auto fast_c, auto snow_c) {
         int64_t t_first = slab.t_begin;
