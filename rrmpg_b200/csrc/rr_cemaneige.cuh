@@ -118,6 +118,9 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
     if (EXACT) L = LC;
     double G[LC], eTG[LC];
     double sca_prev[HYST ? LC : 1], swe_max[HYST ? LC : 1], thmelt[HYST ? LC : 1], fice[ICE ? LC : 1];
+    // hysteresis contract step: reciprocal of the current ablation threshold min(swe_max, Psolannual Rsp) per layer;
+    // 0 = stale (swe_max changed), < 0 = threshold outside [2^-60, 2^60] (IEEE division instead)
+    double yth[HYST ? LC : 1];
 #pragma unroll
     for (int l = 0; l < LC; ++l) {
         G[l] = 0.0;
@@ -126,6 +129,7 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
             // sca[t-1] at t = 0 is sca[T-1], still 0 from np.zeros -- or sca_init itself when T == 1 (:126)
             sca_prev[l] = (a.T == 1) ? sca0 : 0.0;
             swe_max[l] = 0.0;
+            yth[l] = 0.0;
             thmelt[l] = ((l < L) ? g_tresh[kCemaMaxLayers + l] : 0.0) * Rsp;  // Psolannual * Rsp, :139
         }
         if (ICE) fice[l] = (l < L) ? a.frac_ice[cb * a.L + l] : 0.0;
@@ -210,6 +214,22 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
             }
         }
     }
+    // ---- Hysteresis-routine contract (round 2), same idea: Kf >= 0, Thacc within [2^-60, 2^60], finite non-negative
+    // Rsp / initial states, finite forcing with non-negative snow and rain.  Then the pack, the snow-covered area and
+    // both quotients of cemaneigehyst_model.py:135,149 are finite and non-negative for the whole series, and the step
+    // needs neither the max(sca, 0) nor the min(melt, G) of :154,160 (0.9 sca + 0.1 <= 1 for sca <= 1 and RN is
+    // monotonic, so melt <= pot_melt <= G), divides by Thacc with the unchecked Markstein sequence and by the ablation
+    // threshold through a per-layer reciprocal that is refreshed only when swe_max changed.  Bit-identical.
+    bool hyst_ok = false;
+    if constexpr (HYST) {
+        hyst_ok = Kf >= 0.0 && Kf <= 1e6 && fabs(CTG) <= 1e6 && thacc_span != 0u && Rsp >= 0.0 && Rsp <= 1e6 &&
+                  g0 >= 0.0 && g0 <= 1e6 && fabs(e0) <= 1e6 && sca0 >= 0.0 && sca0 <= 1e6 && *fflag == 0u;
+#pragma unroll
+        for (int l = 0; l < LC; ++l)
+            if (l < L)
+                hyst_ok = hyst_ok && G[l] >= 0.0 && G[l] <= 1e13 && fabs(eTG[l]) <= 1e6 && sca_prev[l] >= 0.0 &&
+                          sca_prev[l] <= 1e6 && swe_max[l] >= 0.0 && swe_max[l] <= 1e13 && thmelt[l] >= 0.0 && thmelt[l] <= 1e13;
+    }
     uint32_t tb = 0;
     bool use_fast = false;
     Exp2Regs ek{};
@@ -234,6 +254,7 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
             ek = load_exp2_regs(tb);
             gr.enter_fast();
         }
+        if constexpr (HYST) hyst_ok = __syncthreads_and(hyst_ok) != 0;
     } else if constexpr (!COUPLED && !HYST) {
         use_fast = __syncthreads_and(snow_ok) != 0;  // standalone Cemaneige: the contract step in both math modes
     }
@@ -290,6 +311,45 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
                         }
                     }
                     melt = (0.9 * ratio + 0.1) * pot;                     // :115
+                } else if constexpr (CONTRACT) {
+                    // hysteresis routine under the contract above (cemaneigehyst_model.py:117-167)
+                    const double kt = Kf * Tm;
+                    const double capped = (kt > g) ? g : kt;
+                    const double pot = (e == 0 && Tm > 0) ? capped : 0.0;
+                    const double bal = snow - pot;                        // :131
+                    double sca;
+                    if (bal >= 0) {                                       // accumulation, :133-136
+                        double q = bal * inv_thacc;                        // RN(bal / Thacc), div_by_invariant unchecked
+                        double r = fma(-Thacc, q, bal);
+                        q = fma(r, inv_thacc, q);
+                        r = fma(-Thacc, q, bal);
+                        q = fma(r, inv_thacc, q);
+                        sca = sca_prev[l] + q;
+                        if (g > swe_max[l]) {                             // max(swe_max, G) = (G > swe_max) ? G : swe_max
+                            swe_max[l] = g;
+                            yth[l] = 0.0;
+                        }
+                    } else {                                              // ablation, :138-151
+                        const double thmax = (swe_max[l] > thmelt[l]) ? thmelt[l] : swe_max[l];
+                        double y = yth[l];
+                        if (y == 0.0) {  // first ablation step since swe_max changed: one IEEE reciprocal
+                            y = (thmax >= 0x1p-60 && thmax <= 0x1p60) ? 1.0 / thmax : -1.0;
+                            yth[l] = y;
+                        }
+                        if (y > 0.0) {                                    // RN(G / Thmax), G = 0 or within [2^-452, 1e13]
+                            double q = g * y;
+                            double r = fma(-thmax, q, g);
+                            q = fma(r, y, q);
+                            r = fma(-thmax, q, g);
+                            sca = fma(r, y, q);
+                        } else {
+                            sca = (thmax > 0) ? g / thmax : 0.0;
+                        }
+                    }
+                    sca = nb_min(sca, 1.0);                               // :154, sca >= 0 under the contract
+                    melt = (0.9 * sca + 0.1) * pot;                       // :157; <= pot <= G, so :160 is the identity
+                    sca_prev[l] = sca;
+                    if (STORAGE) st_stream(S_o + (int64_t)l * stride, sca);
                 } else {
                     // potential melt (cemaneigehyst_model.py:117-128), branch-free
                     const double kt = Kf * Tm;
@@ -312,7 +372,10 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
                     if (STORAGE) st_stream(S_o + (int64_t)l * stride, sca);
                 }
                 g = g - melt;                                             // :118 / hyst :163
-                if (HYST && g == 0) swe_max[l] = 0.0;                     // hyst :166-167
+                if (HYST && g == 0) {                                     // hyst :166-167
+                    swe_max[l] = 0.0;
+                    yth[l] = 0.0;
+                }
                 lw_sum += rain + melt;                                    // :121, :125
                 if (ICE) {                                                // icemelt_model.py:52-62
                     double im = DDF * Tm;                                 // temp - tbase, tbase = 0
@@ -394,8 +457,12 @@ __global__ void RRB_CEMA_BOUNDS cema_kernel(CemaArgs a, CemaOut out, Slab slab, 
             }
         });
     };
-    if constexpr (COUPLED && FAST) {
-        if (use_fast) run(ic<1>{}, ic<HYST ? 0 : 1>{});
+    if constexpr (COUPLED && FAST && HYST) {
+        if (use_fast && hyst_ok) run(ic<1>{}, ic<1>{});
+        else if (use_fast) run(ic<1>{}, ic<0>{});
+        else run(ic<0>{}, ic<0>{});
+    } else if constexpr (COUPLED && FAST) {
+        if (use_fast) run(ic<1>{}, ic<1>{});
         else run(ic<0>{}, ic<0>{});
     } else if constexpr (!COUPLED && !HYST) {
         if (use_fast) run(ic<0>{}, ic<1>{});

@@ -23,12 +23,16 @@
 #include "rr_objective.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 #ifndef RRB_HBV_DEFAULT_VARIANT
 #define RRB_HBV_DEFAULT_VARIANT 2
 #endif
 #ifndef RRB_HBV_PIPELINE
 #define RRB_HBV_PIPELINE 0
+#endif
+#ifndef RRB_HBV_HORNER
+#define RRB_HBV_HORNER 0  // measured: 3.06 vs 2.88 ms at 65 536 members (the uniform-register constants bring BRA.DIV back)
 #endif
 
 namespace rrb {
@@ -237,7 +241,8 @@ struct HbvPowK {  // polynomial coefficients held in registers (an FMA takes one
 
 // ABL: timing ablations for the discharge-only instantiation (development builds only, results are WRONG):
 //   1 no output stores, 2 never wet, 3 always wet, 4 table loads replaced by constants
-template <int MPT, bool WRITEQ, bool STORAGE, bool OBJ, int ABL = 0>
+// OBJ: 0 = no fused objective, 1 = MSE / NSE (one sum), 2 = KGE (four sums)
+template <int MPT, bool WRITEQ, bool STORAGE, int OBJ, int ABL = 0>
 __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                                  const double* __restrict__ params, int64_t N, HbvOut out, Slab slab, Objective obj,
                                  Batch batch, uint32_t* __restrict__ fflag) {
@@ -281,7 +286,7 @@ __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, dou
     }
 
     double snow[MPT], soil[MPT], s1[MPT], s2[MPT];
-    ObjAcc acc[MPT];
+    typename std::conditional<OBJ == 2, ObjAccKge, ObjAccSse>::type acc[MPT];
 #pragma unroll
     for (int m = 0; m < MPT; ++m) { snow[m] = snow0; soil[m] = soil0; s1[m] = s10; s2[m] = s20; acc[m].reset(); }  // hbvedu_model.py:78-81
     int64_t t_first = slab.t_begin;
@@ -351,7 +356,7 @@ __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, dou
         double liquid[GP][MPT], pe[GP][MPT], pew[GP][MPT], snow_g[GP][MPT];
         bool need[GP];
     };
-    AOut cur;             // A results of the group whose B phase runs next
+    AOut cur = {};        // A results of the group whose B phase runs next
     int64_t t_cur = 0;    // first timestep of `cur`
     bool pending = false; // `cur` holds A results whose B phase has not run yet
 
@@ -412,6 +417,19 @@ __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, dou
             }
 #pragma unroll
             for (int m = 0; m < MPT; ++m) r[m] = fma(mant[m], invc[m], -1.0);
+#if RRB_HBV_HORNER
+            // Horner with ONE register-resident coefficient per polynomial: every other coefficient is a constant-bank
+            // operand, so each step reads two registers instead of three (the binding resource)
+            double t3[MPT], t2[MPT], t1[MPT];
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) t3[m] = fma(r[m], A4, pk.a3);
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) t2[m] = fma(t3[m], r[m], A2);
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) t1[m] = fma(t2[m], r[m], A1);
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) Lg[m] = fma(r[m], t1[m], kml[m] + log2c[m]);
+#else
 #pragma unroll
             for (int m = 0; m < MPT; ++m) {
                 const double base = kml[m] + log2c[m];
@@ -421,6 +439,7 @@ __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, dou
                 const double t = fma(r2, pb, pa);
                 Lg[m] = fma(r[m], t, base);
             }
+#endif
 #pragma unroll
             for (int m = 0; m < MPT; ++m) {  // 2^(Beta Lg) = scale (1 + rr gg)
                 kd[m] = fma(Beta[m], Lg[m], kShift);
@@ -439,9 +458,14 @@ __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, dou
             }
 #pragma unroll
             for (int m = 0; m < MPT; ++m) {
+#if RRB_HBV_HORNER
+                const double e = fma(rr[m], C3, pk.c2);
+                const double gg = fma(e, rr[m], C1);
+#else
                 const double q2 = rr[m] * rr[m];
                 const double e = fma(rr[m], pk.c2, pk.c1);
                 const double gg = fma(q2, pk.c3, e);
+#endif
                 const double u = rr[m] * gg;
                 w[m] = fma(a.liquid[g][m], u, a.liquid[g][m]);
             }
@@ -621,12 +645,18 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
     uint32_t* wflag = const_cast<uint32_t*>(fflag);
     {
         const size_t smem = smem_ring + hbv_tables_smem_bytes();
-#define RRB_HBV_FAST2A(Q_, S_, O_) hbv_fast2_kernel<1, Q_, S_, O_><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag)
-#define RRB_HBV_FAST2B(Q_, S_, O_) hbv_fast2_kernel<2, Q_, S_, O_><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag)
+        const bool kge = ob && obj.kind == RRB_OBJ_KGE_;  // four running sums instead of one
+#define RRB_HBV_FAST2(M_, Q_, S_, O_)                                                                                  \
+    do {                                                                                                              \
+        if (kge) hbv_fast2_kernel<M_, Q_, S_, (O_) ? 2 : 0><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag);   \
+        else hbv_fast2_kernel<M_, Q_, S_, (O_) ? 1 : 0><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag);       \
+    } while (0)
+#define RRB_HBV_FAST2A(Q_, S_, O_) RRB_HBV_FAST2(1, Q_, S_, O_)
+#define RRB_HBV_FAST2B(Q_, S_, O_) RRB_HBV_FAST2(2, Q_, S_, O_)
 #ifdef RRB_HBV_ABLATIONS
         const int abl = cfg.variant / 16;
         if (abl > 0 && wq && !st && !ob) {
-#define RRB_HBV_ABL(M_, A_) hbv_fast2_kernel<M_, true, false, false, A_><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag)
+#define RRB_HBV_ABL(M_, A_) hbv_fast2_kernel<M_, true, false, 0, A_><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag)
             if (mpt == 2) { if (abl == 1) RRB_HBV_ABL(2, 1); else if (abl == 2) RRB_HBV_ABL(2, 2); else if (abl == 3) RRB_HBV_ABL(2, 3); else RRB_HBV_ABL(2, 4); }
             else { if (abl == 1) RRB_HBV_ABL(1, 1); else if (abl == 2) RRB_HBV_ABL(1, 2); else if (abl == 3) RRB_HBV_ABL(1, 3); else RRB_HBV_ABL(1, 4); }
 #undef RRB_HBV_ABL
@@ -636,6 +666,7 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
         else RRB_HBV_DISPATCH(RRB_HBV_FAST2A);
 #undef RRB_HBV_FAST2A
 #undef RRB_HBV_FAST2B
+#undef RRB_HBV_FAST2
         p_div = mpt;  // the PRECISE launch honours the per-CTA flags
     }
     cudaError_t e = cudaGetLastError();

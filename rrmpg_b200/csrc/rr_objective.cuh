@@ -18,6 +18,60 @@
 
 namespace rrb {
 
+// Lean variant for kernels that template on the metric (HBV-Edu): MSE and NSE need the one sum only, and a KGE
+// accumulator that is never used still costs six registers per member.
+struct ObjAccSse {
+    double sse;
+    __device__ __forceinline__ void reset() { sse = 0.0; }
+    __device__ __forceinline__ void load(const double* state, int64_t slot, int64_t N, int64_t i, const Objective&) {
+        sse = state[slot * N + i];
+    }
+    __device__ __forceinline__ void save(double* state, int64_t slot, int64_t N, int64_t i, const Objective&) const {
+        state[slot * N + i] = sse;
+    }
+    __device__ __forceinline__ void add(double obs, double sim, const Objective&) {
+        const double d = obs - sim;
+        sse += d * d;
+    }
+    __device__ __forceinline__ double finish(const Objective& o) const {
+        const double n = (double)o.T;
+        return (o.kind == RRB_OBJ_NSE_) ? 1.0 - sse / (n * o.obs_std * o.obs_std) : sse / n;
+    }
+};
+
+// KGE only, for kernels that template on the metric: three sums, no branch in the time loop (a CTA-uniform branch
+// would still cut the straight-line group bodies of hbv_fast2_kernel into short basic blocks)
+struct ObjAccKge {
+    double se, see, seo;
+    __device__ __forceinline__ void reset() { se = see = seo = 0.0; }
+    __device__ __forceinline__ void load(const double* state, int64_t slot, int64_t N, int64_t i, const Objective&) {
+        se = state[(slot + 1) * N + i];
+        see = state[(slot + 2) * N + i];
+        seo = state[(slot + 3) * N + i];
+    }
+    __device__ __forceinline__ void save(double* state, int64_t slot, int64_t N, int64_t i, const Objective&) const {
+        state[(slot + 1) * N + i] = se;
+        state[(slot + 2) * N + i] = see;
+        state[(slot + 3) * N + i] = seo;
+    }
+    __device__ __forceinline__ void add(double obs, double sim, const Objective& o) {
+        const double e = sim - o.obs_mean;
+        se += e;
+        see = fma(e, e, see);
+        seo = fma(e, obs - o.obs_mean, seo);
+    }
+    __device__ __forceinline__ double finish(const Objective& o) const {
+        const double n = (double)o.T;
+        const double me = se / n;
+        const double var = see / n - me * me;
+        const double sd = sqrt(var > 0.0 ? var : 0.0);
+        const double r = (seo / n) / (sd * o.obs_std);
+        const double alpha = sd / o.obs_std;
+        const double beta = (o.obs_mean + me) / o.obs_mean;
+        return 1.0 - sqrt((r - 1.0) * (r - 1.0) + (alpha - 1.0) * (alpha - 1.0) + (beta - 1.0) * (beta - 1.0));
+    }
+};
+
 struct ObjAcc {
     double sse, se, see, seo;
     __device__ __forceinline__ void reset() { sse = se = see = seo = 0.0; }

@@ -1,7 +1,7 @@
 // d2h_probe.cu -- what the box's host link gives the end-to-end path: concurrent pinned device-to-host copies on
 // 1..G GPUs, 1/2/4 streams per device, 128 MB slabs (the shape of run_job's slab ring, rr_api.cu).  The aggregate
 // GB/s per device count is the ceiling `e2e` is reported against.
-// Build: nvcc -arch=sm_100a -O3 -o d2h_probe d2h_probe.cu ; usage: d2h_probe [max_devices] [slab_MB] [slabs_per_device]
+// Build: nvcc -arch=sm_100a -O3 -o d2h_probe d2h_probe.cu ; usage: d2h_probe [max_devices] [slab_MB] [slabs_per_device] [d2h-only]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +18,7 @@ int main(int argc, char** argv) {
     if (ndev > max_dev) ndev = max_dev;
     const size_t slab = (size_t)(argc > 2 ? atoi(argv[2]) : 128) << 20;
     const int slabs = argc > 3 ? atoi(argv[3]) : 16;  // 2 GB per device per measurement
+    const bool quick = argc > 4;  // "d2h-only": default pinned memory, device-to-host only, one stream per device
     const int kMaxStreams = 4;
     printf("devices %d, slab %zu MB, %d slabs per device per measurement\n", ndev, slab >> 20, slabs);
     std::vector<char*> dbuf(ndev);
@@ -29,6 +30,7 @@ int main(int argc, char** argv) {
         for (int s = 0; s < kMaxStreams; ++s) CK(cudaStreamCreateWithFlags(&st[d][s], cudaStreamNonBlocking));
     }
     for (unsigned flags : {(unsigned)cudaHostAllocDefault, (unsigned)cudaHostAllocPortable}) {
+        if (quick && flags != cudaHostAllocDefault) break;
         // one host buffer per device, large enough that every slab lands on fresh pages (no cache-resident target)
         std::vector<char*> hbuf(ndev);
         for (int d = 0; d < ndev; ++d) {
@@ -36,9 +38,10 @@ int main(int argc, char** argv) {
             CK(cudaHostAlloc((void**)&hbuf[d], slab * slabs, flags));
             for (size_t o = 0; o < slab * slabs; o += 4096) hbuf[d][o] = 0;  // touch
         }
-        for (int dir = 0; dir < 2; ++dir)
-            for (int g = 1; g <= ndev; g *= 2)
+        for (int dir = 0; dir < (quick ? 1 : 2); ++dir)
+            for (int g = quick ? ndev : 1; g <= ndev; g *= 2)
                 for (int ns : {1, 2, 4}) {
+                    if (quick && ns != 1) break;
                     double best = 0;
                     for (int rep = 0; rep < 3; ++rep) {
                         for (int d = 0; d < g; ++d) { CK(cudaSetDevice(d)); CK(cudaDeviceSynchronize()); }
@@ -63,7 +66,7 @@ int main(int argc, char** argv) {
         for (int d = 0; d < ndev; ++d) { CK(cudaSetDevice(d)); CK(cudaFreeHost(hbuf[d])); }
     }
     // a plain host memcpy of the same size: what one core moves (the numpy-side copy some callers add afterwards)
-    {
+    if (!quick) {
         char* a = (char*)malloc(slab * 4); char* b = (char*)malloc(slab * 4);
         for (size_t o = 0; o < slab * 4; o += 4096) { a[o] = 1; b[o] = 0; }
         auto t0 = std::chrono::steady_clock::now();
