@@ -47,9 +47,10 @@ def test_header_is_plain_c():
 
 
 def test_opts_struct_layout_matches_header():
-    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "rrmpg_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
-           'sizeof(rrb_opts), offsetof(rrb_opts, stream), offsetof(rrb_opts, block), offsetof(rrb_opts, x4_max),'
-           'offsetof(rrb_opts, qobs), offsetof(rrb_opts, mse), offsetof(rrb_opts, slab_steps));return 0;}\n')
+    fields = ["stream", "block", "variant", "x4_max", "qobs", "mse", "slab_steps", "objective", "n_devices", "devices",
+              "obs_stats", "state_in", "state_out", "out_row_pitch"]
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "rrmpg_b200.h"\nint main(void){printf("%zu", sizeof(rrb_opts));'
+           + "".join(f'printf(" %zu", offsetof(rrb_opts, {f}));' for f in fields) + 'printf("\\n");return 0;}\n')
     exe = os.path.join(ROOT, "oracle", "_layout_probe")
     r = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-x", "c", "-", "-o", exe], input=src,
                        capture_output=True, text=True)
@@ -59,8 +60,7 @@ def test_opts_struct_layout_matches_header():
     finally:
         os.remove(exe)
     O = _lib.Opts
-    assert got == [C.sizeof(O), O.stream.offset, O.block.offset, O.x4_max.offset, O.qobs.offset, O.mse.offset,
-                   O.slab_steps.offset]
+    assert got == [C.sizeof(O)] + [getattr(O, f).offset for f in fields]
 
 
 @pytest.mark.skipif(_lib.device_count() > 0, reason="a GPU is present")

@@ -42,6 +42,8 @@ def _worker(rank, world, port, out_dir):
     slow = rdist.max_over_ranks(float(rank + 1))
     assert slow == float(world)
     rdist.barrier()
+    rdist.host_barrier()     # the host-side (gloo) barrier bench.py's e2e leg waits on
+    assert rdist.host_group() is not None
     dist.destroy_process_group()
 
 

@@ -266,3 +266,50 @@ def test_vectorised_fit_driver_polishes_with_batched_gradients():
     assert (3, 4) in shapes                             # the polish step: k + 1 members per gradient
     rough = _fit.minimise(loss, bounds, (2.0,), de_kwargs=dict(seed=3, maxiter=30, tol=1e-3, polish=False))
     assert res.fun <= rough.fun and res.nfev > rough.nfev
+
+
+# ------------------------------------------------------------------ round 2: host-side logic of the new options (no GPU)
+def test_fused_objective_argument_errors_are_raised_before_the_library_call():
+    from rrmpg_b200 import engine
+    f = dict(temp=np.zeros(20), prec=np.ones(20), month0=np.zeros(20, np.int8), PE_m=np.ones(12), T_m=np.zeros(12))
+    P = np.ones((3, 11))
+    args = (f["temp"], f["prec"], f["month0"], f["PE_m"], f["T_m"], (0, 100, 3, 10), P)
+    with pytest.raises(RuntimeError, match="Nash-Sutcliffe"):          # rrmpg/utils/metrics.py:66-70
+        engine.hbvedu(*args, qobs=np.full(20, 2.0), objective="nse")
+    with pytest.raises(RuntimeError, match="mean of the observations"):  # :166-168
+        engine.hbvedu(*args, qobs=np.r_[np.ones(10), -np.ones(10)], objective="kge")
+    with pytest.raises(RuntimeError, match="standard deviation"):        # :170-173
+        engine.hbvedu(*args, qobs=np.full(20, 2.0), objective="kge")
+    with pytest.raises(ValueError, match="objective must be one of"):
+        engine.hbvedu(*args, qobs=np.arange(20.0), objective="rmse")
+    with pytest.raises(ValueError, match="Arrays must have the same size"):   # :127-128
+        engine.hbvedu(*args, qobs=np.arange(19.0))
+    with pytest.raises(ValueError, match="month0 must be"):
+        engine.hbvedu(f["temp"], f["prec"], np.full(20, 12, np.int8), f["PE_m"], f["T_m"], (0, 100, 3, 10), P)
+    with pytest.raises(ValueError, match="devices must be"):
+        engine.hbvedu(*args, devices="every")
+
+
+def test_fused_context_and_monte_carlo_argument_handling():
+    from rrmpg_b200 import engine
+    from rrmpg_b200.tools import monte_carlo
+    with engine.fused(np.ones(4)):
+        with pytest.raises(RuntimeError, match="do not nest"):
+            with engine.fused(np.ones(4)):
+                pass
+    assert engine._FUSED is None
+    with pytest.raises(ValueError, match="needs qobs"):
+        monte_carlo(ABCModel(), num=3, return_qsim=False, prec=np.ones(5))
+    with pytest.raises(TypeError):
+        monte_carlo(object(), num=3)
+    with pytest.raises(TypeError):
+        monte_carlo(ABCModel(), num=0)
+
+
+def test_state_row_layout_of_the_resumable_models():
+    from rrmpg_b200 import _lib
+    L = _lib.lib()
+    assert L.rrb_state_rows(_lib.MODEL_ABC, 0.0) == 1
+    assert L.rrb_state_rows(_lib.MODEL_HBVEDU, 0.0) == 4
+    assert [L.rrb_state_rows(_lib.MODEL_GR4J, x) for x in (2.9, 3.0, 3.5, 10.0, 64.0)] == [12, 12, 15, 33, 2 + 64 + 129]
+    assert L.rrb_state_rows(_lib.MODEL_GR4J, 65.0) == -1 and L.rrb_state_rows(99, 1.0) == -1
