@@ -103,7 +103,9 @@ typedef struct rrb_opts {
                             the call returns without synchronising */
     int32_t block;       /* threads per CTA, 0 = chosen from N and the SM count */
     int32_t variant;     /* kernel variant, for A/B timing only: 0 = the library's choice.  HBV-Edu FAST: 1 = one member per
-                            thread, 2 = two members per thread (needs an even N and 16-byte aligned rows, else 1) */
+                            thread, 2 = two members per thread (needs an even N and 16-byte aligned rows, else 1), 3 = the
+                            rotating schedule (hbv_rot_kernel; at most 16 member-warps per SM, no storage outputs, else 2),
+                            5 = two members per thread as ONE CTA per SM (at most 16 member-warps per SM, else 2) */
     double x4_max;       /* RRB_MEM_DEVICE, GR4J family: max x4 over params if the caller knows it;
                             <= 0 lets the library reduce it on the device (one small sync) */
     const double* qobs;  /* optional [T] observed discharge: fuses the objective into the kernel */

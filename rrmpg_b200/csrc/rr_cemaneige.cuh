@@ -510,11 +510,19 @@ static cudaError_t cema_launch_variant(const CemaArgs& a, const CemaOut& out, co
                                        const LaunchCfg& cfg) {
     constexpr int R = CemaGeom<LC>::R, TT = CemaGeom<LC>::TT;
     int block = cfg.block > 0 ? cfg.block : pick_block(a.N * a.count, cfg.sm_count, a.N >= 128 ? 128 : 64);
+    const bool plain = out.q && !out.G && !obj.qobs;
+    if (cfg.block <= 0 && a.count == 1 && Gr4j::kOrdSmemBytes == 0) {  // 9 .. 16 warps per SM: one CTA per SM (rr_kernels.h)
+        int cap;
+        if (plain && a.L == LC) cap = kernel_max_threads(cema_kernel<LC, Gr4j, FAST, true, true, FAMILY>);
+        else if (FAMILY == 0 && a.L == LC) cap = kernel_max_threads(cema_kernel<LC, Gr4j, FAST, false, true, FAMILY>);
+        else cap = kernel_max_threads(cema_kernel<LC, Gr4j, FAST, false, false, FAMILY>);
+        const int b = one_cta_block(a.N, cfg.sm_count, cap < 512 ? cap : 512, 9);
+        if (b) block = b;
+    }
     if (Gr4j::kOrdSmemBytes > 0 && block > kOrdThreads) block = kOrdThreads;  // ordinate columns in shared memory
     const dim3 grid((unsigned)((a.N + block - 1) / block), (unsigned)a.count);
     const size_t smem = forcing_smem_bytes<R, TT>() + ((FAMILY & 1) ? 0 : 32 * LC) +
                         ((FAST && Gr4j::kStateSlots > 0) ? fastmath_smem_bytes() : 0) + Gr4j::kOrdSmemBytes;
-    const bool plain = out.q && !out.G && !obj.qobs;
 #define RRB_CEMA(P_, E_) cema_kernel<LC, Gr4j, FAST, P_, E_, FAMILY><<<grid, block, smem, cfg.stream>>>(a, out, slab, obj)
     if (FAMILY == 0) {
         if (plain && a.L == LC) RRB_CEMA(true, true);

@@ -167,11 +167,17 @@ static cudaError_t launch_variant(const double* F, int64_t T, double s_init, dou
                                   double* qsim, double* s_store, double* r_store, const Slab& slab,
                                   const Objective& obj, const LaunchCfg& cfg, const Batch& batch) {
     int block = cfg.block > 0 ? cfg.block : pick_block(N * batch.count, cfg.sm_count, N >= 128 ? 128 : 64);
+    const bool plain = qsim && !s_store && !obj.qobs;
+    if (cfg.block <= 0 && batch.count == 1 && Member::kOrdSmemBytes == 0) {  // 9 .. 16 warps per SM: one CTA per SM
+        const int cap = plain ? kernel_max_threads(gr4j_kernel<Member, FAST, true>) : kernel_max_threads(gr4j_kernel<Member, FAST, false>);
+        const int b = one_cta_block(N, cfg.sm_count, cap < 512 ? cap : 512, 9);
+        if (b) block = b;
+    }
     if (Member::kOrdSmemBytes > 0 && block > kOrdThreads) block = kOrdThreads;  // ordinate columns in shared memory
     const dim3 grid((unsigned)((N + block - 1) / block), (unsigned)batch.count);
     const size_t smem = forcing_smem_bytes<kGr4jR, kGr4jTT>() + (FAST ? fastmath_smem_bytes() : 0) + Member::kOrdSmemBytes;
     const uint32_t* fflag = forcing_flag(F, T, kGr4jTT, kGr4jR);
-    if (qsim && !s_store && !obj.qobs)
+    if (plain)
         gr4j_kernel<Member, FAST, true><<<grid, block, smem, cfg.stream>>>(F, s_init, r_init, params, N, qsim, s_store,
                                                                            r_store, slab, obj, fflag, batch);
     else

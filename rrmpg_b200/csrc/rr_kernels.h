@@ -57,6 +57,23 @@ struct Objective {
 };
 
 int pick_block(int64_t N, int sm_count, int max_block);
+// ONE CTA per SM for a mid-sized single-catchment launch: warp w of a CTA that has an SM to itself runs on sub-partition
+// w % 4, so a CTA of ceil(warps / SMs) warps spreads the ensemble evenly over the four sub-partitions of every SM -- the
+// hardware's own placement of many small CTAs does not (profiles/r02_layout_sweep.txt, r02_time_blocks.txt: HBV-Edu up to
+// +40 %, GR4J +11 %, Cemaneige +4 % at 65 536 members).  Returns the CTA size, or 0 when the layout does not apply: fewer
+// than min_warps or more than max_threads / 32 warps per SM (max_threads: what the kernel's register count admits).
+inline int one_cta_block(int64_t threads, int sm_count, int max_threads, int min_warps) {
+    if (sm_count <= 0) sm_count = 148;
+    const int64_t warps = (threads + 31) / 32;
+    const int64_t per_sm = (warps + sm_count - 1) / sm_count;
+    if (per_sm < min_warps || per_sm * 32 > max_threads || per_sm > 32) return 0;
+    return (int)per_sm * 32;
+}
+template <class Kernel>
+inline int kernel_max_threads(Kernel k) {
+    cudaFuncAttributes fa{};
+    return cudaFuncGetAttributes(&fa, k) == cudaSuccess ? fa.maxThreadsPerBlock : 0;
+}
 
 // ---- forcing tile geometry (doubles per timestep R, timesteps per tile TT) ----
 constexpr int kAbcR = 1, kAbcTT = 512;

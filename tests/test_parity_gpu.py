@@ -828,14 +828,15 @@ def test_multi_catchment_host_ring_with_many_small_chunks(monkeypatch):
 @pytest.fixture
 def hbv_variant():
     """Sets rrb_opts.variant for the calls of one test (1 / 2: hbv_fast2_kernel with one / two members per thread,
-    3: the round-1 kernel) and restores the library default afterwards."""
+    3: hbv_rot_kernel, 5: two members per thread as one CTA per SM; include/rrmpg_b200.h) and restores the library
+    default afterwards."""
     def set_variant(v):
         engine.VARIANT = v
     yield set_variant
     engine.VARIANT = 0
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 5])
 @pytest.mark.parametrize("N", [70, 71, 1000])
 def test_hbvedu_fast_kernel_variants_vs_oracle(variant, N, hbv_variant):
     hbv_variant(variant)
@@ -893,7 +894,7 @@ def test_hbvedu_negative_zero_temperature_with_a_zero_threshold():
     P["T_t"][1::4] = -0.0
     args = (temp, f["prec"], f["month"] - 1, f["PE_m"], f["T_m"], (5.0, 100, 3, 10), P)
     ref = oracle.hbvedu(*args, return_storage=True)
-    for v in (1, 2, 3):
+    for v in (1, 2, 3, 5):
         engine.VARIANT = v
         try:
             got = engine.hbvedu(*args, return_storage=True)
@@ -901,3 +902,57 @@ def test_hbvedu_negative_zero_temperature_with_a_zero_threshold():
             engine.VARIANT = 0
         for nm, r in zip(["qsim", "snow", "soil", "s1", "s2"], ref):
             assert_close(got[nm], r, f"variant {v} {nm}")
+
+
+# ------------------------------------------------------------------ round 2: launch layouts of the HBV-Edu FAST kernel
+@pytest.mark.parametrize("sms,pairs", [(4, 7), (4, 6), (4, 5), (3, 3), (2, 8), (2, 1), (4, 11), (2, 14), (2, 16), (3, 13)])
+def test_hbvedu_rotating_schedule_and_one_cta_layout_are_bit_identical(sms, pairs, hbv_variant, monkeypatch):
+    """hbv_rot_kernel (variant 3: one persistent CTA per SM, the member pairs rotate over its warps, fast warps stop on a
+    shared-memory counter, per-warp TMA rings) and the one-CTA-per-SM launch of hbv_fast2_kernel<2> (variant 5) run the
+    arithmetic of variant 2 member for member: discharge, fused objectives and carried time-slab states must be
+    bit-identical.  RRMPG_B200_HBV_ROT_SMS pretends a GPU of `sms` SMs so that a small ensemble reaches every shape of the
+    schedule (`pairs` warps per CTA: slow / fast warps, 8- and 16-warp instantiations, a ragged last pair)."""
+    monkeypatch.setenv("RRMPG_B200_HBV_ROT_SMS", str(sms))
+    N, T = 64 * pairs * sms - 6, 2301
+    f, P = _hbv_case(T, N, seed=sms * 100 + pairs)
+    qobs = np.abs(np.random.default_rng(5).normal(2.0, 1.0, T))
+    args = (f["temp"], f["prec"], f["month"] - 1, f["PE_m"], f["T_m"], (2.0, 100, 3, 10), P)
+    ref = oracle.hbvedu(*args)
+    for kw in (dict(), dict(qobs=qobs, objective="kge"), dict(qobs=qobs, want_qsim=False),
+               dict(qobs=qobs, objective="nse", slab_steps=777)):
+        hbv_variant(2)
+        base = engine.hbvedu(*args, **kw)
+        if base.get("qsim") is not None:
+            assert_close(base["qsim"], ref, f"variant 2 {sorted(kw)} vs oracle")
+        for v in (3, 5):
+            hbv_variant(v)
+            got = engine.hbvedu(*args, **kw)
+            for nm in base:
+                if base[nm] is not None:
+                    assert_bits_equal(got[nm], base[nm], f"variant {v} sms={sms} pairs={pairs} {sorted(kw)} {nm}")
+
+
+@pytest.mark.parametrize("variant", [3, 5])
+def test_hbvedu_layout_variants_leave_flagged_members_to_the_precise_kernel(variant, hbv_variant, monkeypatch):
+    """Members outside the FAST contract and soil moistures that leave the table range: hbv_rot_kernel flags the pair (64
+    members) and takes it out of its schedule, the one-CTA launch flags its CTA; the PRECISE kernel behind (64-thread
+    CTAs, a whole fraction of a flag word's members) redoes them -- also slab by slab with carried states."""
+    monkeypatch.setenv("RRMPG_B200_HBV_ROT_SMS", "3")
+    hbv_variant(variant)
+    T, N = 2200, 64 * 7 * 3
+    f, P = _hbv_case(T, N, seed=35)
+    P["FC"][5] = 1e-200          # outside [2^-500, 2^500]
+    P["Beta"][70] = 40.0         # |Beta| >= 32
+    P["K_0"][333] = np.inf
+    P["FC"][450] = 3.5e6         # soil/FC below 2^-15 from the first step on
+    P["FC"][777] = 1.0e6         # ... and here only after a dry spell (range exit in the middle of the series)
+    P["FC"][N - 1] = -150.0      # negative base of the pow: NaN from the first wet step on
+    qobs = np.abs(np.random.default_rng(6).normal(2.0, 1.0, T))
+    args = (f["temp"], f["prec"], f["month"] - 1, f["PE_m"], f["T_m"], (0.0, 100, 3, 10), P)
+    with np.errstate(all="ignore"):
+        ref = oracle.hbvedu(*args)
+        mse = np.mean((qobs[:, None] - ref) ** 2, axis=0)
+    for slab in (0, 700):
+        got = engine.hbvedu(*args, qobs=qobs, slab_steps=slab)
+        assert_close(got["qsim"], ref, f"variant {variant} slab={slab} qsim")
+        assert_close(got["mse"], mse, f"variant {variant} slab={slab} mse", rtol=1e-9)
