@@ -28,11 +28,8 @@
 #ifndef RRB_HBV_DEFAULT_VARIANT
 #define RRB_HBV_DEFAULT_VARIANT 2
 #endif
-#ifndef RRB_HBV_ONE_CTA_AUTO
-#define RRB_HBV_ONE_CTA_AUTO 1  // 1: mid-sized ensembles (5 .. 16 warps per SM) are launched as one CTA per SM
-#endif
-#ifndef RRB_HBV_ROT_AUTO
-#define RRB_HBV_ROT_AUTO 1  // 1: the library picks hbv_rot_kernel where rot_warps() says it applies
+#ifndef RRB_HBV_SEASONS
+#define RRB_HBV_SEASONS 1  // short A phases for groups that are warm-and-bare or cold for a whole warp (hbv_fast2_loop)
 #endif
 #ifndef RRB_HBV_HORNER
 #define RRB_HBV_HORNER 0  // measured: 3.06 vs 2.88 ms at 65 536 members (the uniform-register constants bring BRA.DIV back)
@@ -340,6 +337,74 @@ __device__ __forceinline__ void hbv_fast2_loop(const HbvPar<MPT>& P, HbvSt<MPT, 
         if constexpr (ABL == 2) o.need[g] = false;
         if constexpr (ABL == 3) o.need[g] = true;
     };
+    // Seasons of a warp.  The snow routine is 17 of the 22 issue slots of A(t) per member, and for most of the year it
+    // does nothing that depends on the member: when the step is warm for EVERY member of the warp (temp above the largest
+    // threshold) and no member has snow left, melt = min(snow, m) = +0, the pack stays empty and the liquid water is the
+    // precipitation; when it is cold for every member, the precipitation joins the pack and there is no liquid water.
+    // Both conditions are warp-uniform (the forcing is the same for all members; tt_hi / tt_lo are warp-reduced once; the
+    // snow-free flag is voted after every full A phase), so the two steps of a group take a short A phase instead -- the
+    // same values bit for bit.  Temperatures are compared through their high words (one integer compare each, an
+    // unordered or borderline value simply takes the full phase).
+    double tt_hi = P.Tt[0], tt_lo = P.Tt[0];
+#pragma unroll
+    for (int m = 1; m < MPT; ++m) { tt_hi = fmax(tt_hi, P.Tt[m]); tt_lo = fmin(tt_lo, P.Tt[m]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tt_hi = fmax(tt_hi, __shfl_xor_sync(0xffffffffu, tt_hi, o));
+        tt_lo = fmin(tt_lo, __shfl_xor_sync(0xffffffffu, tt_lo, o));
+    }
+    // warm for all: hi(temp) > hi(max(tt_hi, +0)) as signed integers (both non-negative then: a larger high word is a larger value)
+    // (a negative degree-day factor would make m = DD (temp - T_t) < 0 = snow: no short phase for such a warp)
+    bool dd_ok = true;
+#pragma unroll
+    for (int m = 0; m < MPT; ++m) dd_ok = dd_ok && !(P.DD[m] < 0.0);
+    int warm_key = __all_sync(0xffffffffu, dd_ok) ? __double2hiint(fmax(tt_hi, 0.0)) : 0x7fffffff;
+    // cold for all: temp < min(tt_lo, -0) <= 0: both negative, a larger high word (unsigned) is a smaller value
+    uint32_t cold_key = (uint32_t)__double2hiint(fmin(tt_lo, -0.0)) | 0x80000000u;
+    pin(cold_key);
+    {
+        uint32_t wk = (uint32_t)warm_key;
+        pin(wk);
+        warm_key = (int)wk;
+    }
+    auto any_snow = [&]() __attribute__((always_inline)) {
+        bool some = false;
+#pragma unroll
+        for (int m = 0; m < MPT; ++m) some = some || ((__double2hiint(S.snow[m]) | __double2loint(S.snow[m])) != 0);
+        return __any_sync(0xffffffffu, some) != 0;
+    };
+    bool snow_free = !any_snow();
+    auto a_potential_et = [&](const HbvF& f, AOut& o, int g) __attribute__((always_inline)) {
+#pragma unroll
+        for (int m = 0; m < MPT; ++m) {
+            o.snow_g[g][m] = S.snow[m];
+            o.pe[g][m] = fma(P.C[m], f.dT, f.PEm);
+            o.pew[g][m] = o.pe[g][m] * P.inv_PWP[m];
+        }
+    };
+    // warm for every member, no snow anywhere: sel = melt = +0, snow - 0 = snow, liquid = prec + 0
+    auto a_warm_bare = [&](const HbvF& f, AOut& o, int g) __attribute__((always_inline)) {
+        const double lq = f.prec + 0.0;  // (-0.0 + +0.0 = +0.0, as in the full phase)
+#pragma unroll
+        for (int m = 0; m < MPT; ++m) o.liquid[g][m] = lq;
+        a_potential_et(f, o, g);
+        o.need[g] = __any_sync(0xffffffffu, (__double2hiint(lq) | __double2loint(lq)) != 0);
+        if constexpr (ABL == 2) o.need[g] = false;
+        if constexpr (ABL == 3) o.need[g] = true;
+    };
+    // cold for every member: sel = -prec, snow - (-prec), liquid = prec + (-prec) = +0 (finite precipitation)
+    auto a_cold = [&](const HbvF& f, AOut& o, int g) __attribute__((always_inline)) {
+        const double nprec = __hiloint2double(__double2hiint(f.prec) ^ (int)0x80000000, __double2loint(f.prec));
+        const double lq = f.prec + nprec;
+#pragma unroll
+        for (int m = 0; m < MPT; ++m) {
+            S.snow[m] = S.snow[m] - nprec;
+            o.liquid[g][m] = lq;
+        }
+        a_potential_et(f, o, g);
+        o.need[g] = false;
+        if constexpr (ABL == 3) o.need[g] = true;
+    };
     // B of step g of group `a`; WET = the warp evaluates the pow for this step
     auto phase_b = [&](auto wet_c, const AOut& a, int g) __attribute__((always_inline)) {
         constexpr bool WET = decltype(wet_c)::value != 0;
@@ -462,12 +527,26 @@ __device__ __forceinline__ void hbv_fast2_loop(const HbvPar<MPT>& P, HbvSt<MPT, 
     run([&](auto gc, int64_t t0, const HbvF* f) __attribute__((always_inline)) {
         constexpr int G = decltype(gc)::value;
         if constexpr (G == GP) {
-            phase_a(f[0], cur, 0);   // A of both steps: four independent short chains per member pair
-            phase_a(f[1], cur, 1);
+            const int h0 = __double2hiint(f[0].temp), h1 = __double2hiint(f[1].temp);
+            const bool warm = snow_free && __all_sync(0xffffffffu, (h0 > warm_key) & (h1 > warm_key));
+            const bool cold = __all_sync(0xffffffffu, ((uint32_t)h0 > cold_key) & ((uint32_t)h1 > cold_key));
+            if (RRB_HBV_SEASONS && warm) {
+                a_warm_bare(f[0], cur, 0);
+                a_warm_bare(f[1], cur, 1);
+            } else if (RRB_HBV_SEASONS && cold) {
+                a_cold(f[0], cur, 0);
+                a_cold(f[1], cur, 1);
+                snow_free = false;
+            } else {
+                phase_a(f[0], cur, 0);   // A of both steps: four independent short chains per member pair
+                phase_a(f[1], cur, 1);
+                if (RRB_HBV_SEASONS) snow_free = !any_snow();
+            }
             t_cur = t0;
             run_group_b();
         } else {  // a ragged step at the edge of a time slab
             phase_a(f[0], cur, 0);
+            if (RRB_HBV_SEASONS) snow_free = !any_snow();
             t_cur = t0;
             if (cur.need[0]) phase_b(ic<1>{}, cur, 0);
             else phase_b(ic<0>{}, cur, 0);
@@ -504,10 +583,10 @@ __device__ __forceinline__ HbvPowK hbv_pow_coefficients(uint32_t tb) {
 // [2^-500, 2^500], |Beta| < 32.  Per launch (forcing flag, set by the packer): finite precipitation and temperature.
 // OBJ: 0 = no fused objective, 1 = MSE / NSE (one sum), 2 = KGE (three sums)
 // ------------------------------------------------------------------------------------------------
-template <int MPT, bool WRITEQ, bool STORAGE, int OBJ, int ABL = 0>
-__global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
-                                 const double* __restrict__ params, int64_t N, HbvOut out, Slab slab, Objective obj,
-                                 Batch batch, uint32_t* __restrict__ fflag) {
+template <int MPT, bool WRITEQ, bool STORAGE, int OBJ, int ABL>
+__device__ __forceinline__ void hbv_fast2_body(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
+                                               const double* __restrict__ params, int64_t N, HbvOut out, Slab slab, Objective obj,
+                                               Batch batch, uint32_t* __restrict__ fflag) {
     if (*fflag != 0u) return;  // non-finite forcing: the PRECISE kernel behind takes the whole launch
     HBV_BATCH_PROLOGUE
     const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -593,6 +672,23 @@ __global__ void hbv_fast2_kernel(const double* __restrict__ F, double snow0, dou
             if (OBJ && obj.mse && slab.t_end >= obj.T) obj.mse[i0 + m] = S.acc[m].finish(obj);
         }
     }
+}
+
+// Two compilations of that body.  hbv_fast2_kernel is held to 128 registers (two 256-thread CTAs or one CTA of up to 16
+// warps per SM); hbv_fast2_wide_kernel is not (154 registers for two members per thread): one CTA per SM of at most 12
+// warps, where it is 11 % faster than the capped build (profiles/r02_seasons_ab.txt, 104 192 members).
+template <int MPT, bool WRITEQ, bool STORAGE, int OBJ, int ABL = 0>
+__global__ void __launch_bounds__(512, 1)
+hbv_fast2_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
+                 const double* __restrict__ params, int64_t N, HbvOut out, Slab slab, Objective obj, Batch batch,
+                 uint32_t* __restrict__ fflag) {
+    hbv_fast2_body<MPT, WRITEQ, STORAGE, OBJ, ABL>(F, snow0, soil0, s10, s20, params, N, out, slab, obj, batch, fflag);
+}
+template <bool WRITEQ, int OBJ>
+__global__ void hbv_fast2_wide_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
+                                      const double* __restrict__ params, int64_t N, HbvOut out, Slab slab, Objective obj,
+                                      Batch batch, uint32_t* __restrict__ fflag) {
+    hbv_fast2_body<2, WRITEQ, false, OBJ, 0>(F, snow0, soil0, s10, s20, params, N, out, slab, obj, batch, fflag);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -997,18 +1093,19 @@ static RotCfg rot_cfg() {
     return c;
 }
 
-// hbv_rot_kernel applies to a single catchment without storage outputs whose pairs (64 members) fit one persistent CTA
-// per SM: P = ceil(pairs / SMs) <= 16 warps.  Measured against the one-CTA-per-SM launch of hbv_fast2_kernel<2>
+// hbv_rot_kernel (rrb_opts.variant = 3) applies to a single catchment without storage outputs whose pairs (64 members) fit
+// one persistent CTA per SM: P = ceil(pairs / SMs) <= 16 warps.  Measured against hbv_fast2_kernel<2> as one CTA per SM
 // (profiles/r02_layout_sweep.txt): +8.6 % at P = 5, +2.2 % at P = 6, nothing at P = 7 (65 536 members: the lone warp of a
-// (2,2,2,1) SM is slowed to 342 cycles per step by the shared-memory traffic of the six others, 285 when alone), and a
-// loss from P = 8 on -- so the library picks it for P = 5 and 6 only, given a window long enough to rotate in.
-// Returns the warps per CTA (8 or 16), 0 = does not apply.
+// (2,2,2,1) SM is slowed to 342 cycles per step by the shared-memory traffic of the six others, 285 when alone;
+// tools/smsp_neighbour_probe.cu), a loss from P = 8 on -- and one member per thread as one CTA per SM beats it everywhere
+// (47 360 members: 2.19 ms against 2.67), so the library never picks it by itself.  Kept as the measured answer to
+// "migrate the chains between sub-partitions".  Returns the warps per CTA (8 or 16), 0 = does not apply.
 static int rot_warps(int64_t N, int64_t steps, int sm_count, bool pair_ok, bool storage, const Batch& batch, bool forced) {
     if (!pair_ok || storage || batch.count != 1 || sm_count <= 0) return 0;
     const int64_t pairs = (N / 2 + 31) / 32;
     const int64_t P = (pairs + sm_count - 1) / sm_count;
     if (P > kRotMaxWarps) return 0;
-    if (!forced && ((P != 5 && P != 6) || steps < 2048)) return 0;
+    (void)steps; (void)forced;
     return P <= 8 ? 8 : 16;
 }
 
@@ -1026,38 +1123,51 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
     const bool pair_ok = (N % 2) == 0 && aligned16(qsim) && aligned16(snow) && aligned16(soil) && aligned16(s1) && aligned16(s2) &&
                          (!slab.state || aligned16(slab.state));
     const int64_t steps = slab.t_end - slab.t_begin;
-    // (test knob: RRMPG_B200_HBV_ROT_SMS pretends a smaller GPU, so that small ensembles reach every shape of the schedule)
-    const int rot_sms = env_int("RRMPG_B200_HBV_ROT_SMS", cfg.sm_count > 0 ? cfg.sm_count : 148);
-    int rotw = 0;
-    if (fast && slab.t_end < (int64_t(1) << 30)) {
-        if (variant == 3) rotw = rot_warps(N, steps, rot_sms, pair_ok, st, batch, true);
-        else if (variant != 1 && variant != 2 && RRB_HBV_ROT_AUTO) rotw = rot_warps(N, steps, rot_sms, pair_ok, st, batch, false);
+    // (test knob: RRMPG_B200_HBV_ROT_SMS pretends a smaller GPU, so that small ensembles reach every launch shape)
+    const int sms = env_int("RRMPG_B200_HBV_ROT_SMS", cfg.sm_count > 0 ? cfg.sm_count : 148);
+    auto warps_per_sm = [&](int64_t threads) { return ((threads + 31) / 32 + sms - 1) / sms; };
+    // ---- which kernel, how many members per thread, which launch shape (profiles/r02_layout_sweep.txt, r02_seasons_ab*.txt)
+    //  * single catchment, up to 16 member-warps per SM (75 776 members on 148 SMs): ONE member per thread -- twice the warps
+    //    hide the latency of the soil chain better than two chains in one warp -- launched as ONE CTA per SM: warp w of a CTA
+    //    that has its SM to itself runs on sub-partition w % 4, so the warps spread evenly, which the hardware's placement
+    //    of many small CTAs does not (65 536 members: 2.62 ms against 2.76 with 128-thread CTAs and 2.84 with two members
+    //    per thread);
+    //  * up to 16 warps per SM with TWO members per thread (151 552 members): one CTA per SM again, the uncapped build
+    //    while its registers admit the CTA (12 warps);
+    //  * beyond: two members per thread, 256-thread CTAs placed by the hardware.
+    //  rrb_opts.variant: 1 / 2 = members per thread with the default CTA shape, 3 = hbv_rot_kernel, 5 = two members per
+    //  thread as one CTA per SM.
+    const bool single = batch.count == 1;
+    int rotw = 0, sm_block = 0;
+    bool wide = false;
+    if (fast && variant == 3 && slab.t_end < (int64_t(1) << 30)) rotw = rot_warps(N, steps, sms, pair_ok, st, batch, true);
+    if (fast && !rotw && single && cfg.block <= 0 && (variant == 5 || (variant != 1 && variant != 2 && variant != 3))) {
+        const int64_t w1 = warps_per_sm(N), w2 = warps_per_sm(N / 2);
+        if (variant != 5 && w1 <= 16) {
+            variant = 1;
+            if (w1 >= 5) sm_block = (int)w1 * 32;
+        } else if (pair_ok && w2 <= 16 && (variant == 5 || w2 >= 5)) {
+            variant = 2;
+            sm_block = (int)w2 * 32;
+            wide = !st && w2 <= 12;
+        }
     }
-    // one CTA per SM (two members per thread): the warps of a mid-sized ensemble then spread evenly over the four
-    // sub-partitions of every SM (warp w -> SMSP w % 4), which CTAs of a fixed size placed by the hardware do not
-    int sm_block = 0;
-    if (fast && !rotw && pair_ok && batch.count == 1 && cfg.block <= 0 && (variant == 5 || (variant != 1 && variant != 2 && RRB_HBV_ONE_CTA_AUTO))) {
-        const int64_t warps = (N / 2 + 31) / 32;
-        const int64_t per_sm = (warps + rot_sms - 1) / rot_sms;
-        if (per_sm <= 16 && (variant == 5 || per_sm >= 5)) sm_block = (int)per_sm * 32;
-    }
-    if (sm_block) variant = 2;
     if (variant != 1 && variant != 2) variant = RRB_HBV_DEFAULT_VARIANT;
     if (variant == 2 && !pair_ok) variant = 1;
     const int mpt = (fast && variant == 2) ? 2 : 1;
     const int64_t nthreads = (N + mpt - 1) / mpt;
     int block = cfg.block > 0 ? cfg.block : pick_block(nthreads * batch.count, cfg.sm_count, nthreads >= 256 ? 256 : 64);
     dim3 grid((unsigned)((nthreads + block - 1) / block), (unsigned)batch.count);
-    if (rotw) {  // one flag word per pair of 32 threads: the PRECISE launch behind uses 64-thread CTAs
+    if (rotw) {  // one flag word per pair of 32 threads
         block = 64;
         grid = dim3((unsigned)((N / 2 + 31) / 32), 1u);
     } else if (sm_block) {
         block = sm_block;
         grid = dim3((unsigned)((nthreads + block - 1) / block), 1u);
     }
-    // PRECISE: one member per thread; behind a rotating / one-CTA-per-SM launch 64-thread CTAs, each a whole fraction of
-    // the members one flag word stands for
-    const int pblock = (rotw || sm_block) ? 64 : block;
+    // PRECISE: one member per thread; behind a rotating / one-CTA-per-SM launch its CTAs are a whole fraction of the
+    // members one flag word stands for
+    const int pblock = rotw ? 64 : (sm_block ? 32 : block);
     const dim3 grid_p((unsigned)((N + pblock - 1) / pblock), (unsigned)batch.count);
     const size_t smem_ring = forcing_smem_bytes<kHbvR, kHbvTT>();
 #define RRB_HBV_ARGS F, inits4[0], inits4[1], inits4[2], inits4[3], params, N, out, slab, obj, batch
@@ -1081,7 +1191,6 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
     }
     uint32_t* wflag = const_cast<uint32_t*>(fflag);
     if (rotw) {
-        const int sms = rot_sms;
         const int64_t pairs = (N / 2 + 31) / 32;
         const int64_t P = (pairs + sms - 1) / sms;
         const dim3 rgrid((unsigned)((pairs + P - 1) / P), 1u);
@@ -1113,7 +1222,8 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
         p_div = 1;
     } else {
         const size_t smem = smem_ring + hbv_tables_smem_bytes();
-        const bool kge = ob && obj.kind == RRB_OBJ_KGE_;  // four running sums instead of one
+        const bool kge = ob && obj.kind == RRB_OBJ_KGE_;  // three running sums instead of one
+        bool wide_done = false;
 #define RRB_HBV_FAST2(M_, Q_, S_, O_)                                                                                  \
     do {                                                                                                              \
         if (kge) hbv_fast2_kernel<M_, Q_, S_, (O_) ? 2 : 0><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag);   \
@@ -1121,21 +1231,24 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
     } while (0)
 #define RRB_HBV_FAST2A(Q_, S_, O_) RRB_HBV_FAST2(1, Q_, S_, O_)
 #define RRB_HBV_FAST2B(Q_, S_, O_) RRB_HBV_FAST2(2, Q_, S_, O_)
-        if (sm_block > 256) {  // does this instantiation's register count admit the CTA?  Else back to the default launch
-            cudaFuncAttributes fa{};
-#define RRB_HBV_QUERY(Q_, S_, O_)                                                          \
-    do {                                                                                   \
-        if (kge) cudaFuncGetAttributes(&fa, hbv_fast2_kernel<2, Q_, S_, (O_) ? 2 : 0>);    \
-        else cudaFuncGetAttributes(&fa, hbv_fast2_kernel<2, Q_, S_, (O_) ? 1 : 0>);        \
+        if (wide) {  // the uncapped build, while its register count admits the CTA
+#define RRB_HBV_WIDE(Q_, O_)                                                                      \
+    do {                                                                                         \
+        auto k_ = hbv_fast2_wide_kernel<Q_, O_>;                                                  \
+        if (kernel_max_threads(k_) >= block) {                                                   \
+            k_<<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag);                          \
+            wide_done = true;                                                                    \
+        }                                                                                        \
     } while (0)
-            RRB_HBV_DISPATCH(RRB_HBV_QUERY);
-#undef RRB_HBV_QUERY
-            if (fa.maxThreadsPerBlock < sm_block) {
-                LaunchCfg c2 = cfg;
-                c2.variant = 2;
-                return launch_hbvedu(F, T, inits4, params, N, qsim, snow, soil, s1, s2, slab, obj, c2, fflag, batch);
-            }
+            if (wq && !ob) RRB_HBV_WIDE(true, 0);
+            else if (wq && !kge) RRB_HBV_WIDE(true, 1);
+            else if (wq) RRB_HBV_WIDE(true, 2);
+            else if (!kge) RRB_HBV_WIDE(false, 1);
+            else RRB_HBV_WIDE(false, 2);
+#undef RRB_HBV_WIDE
         }
+        if (wide_done) {
+        } else
 #ifdef RRB_HBV_ABLATIONS
         const int abl = cfg.variant / 16;
         if (abl > 0 && wq && !st && !ob) {
@@ -1150,7 +1263,7 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
 #undef RRB_HBV_FAST2A
 #undef RRB_HBV_FAST2B
 #undef RRB_HBV_FAST2
-        p_div = sm_block ? sm_block / 32 : mpt;  // the PRECISE launch honours the per-CTA flags
+        p_div = sm_block ? mpt * sm_block / 32 : mpt;  // the PRECISE launch honours the per-CTA flags
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -908,9 +908,10 @@ def test_hbvedu_negative_zero_temperature_with_a_zero_threshold():
 @pytest.mark.parametrize("sms,pairs", [(4, 7), (4, 6), (4, 5), (3, 3), (2, 8), (2, 1), (4, 11), (2, 14), (2, 16), (3, 13)])
 def test_hbvedu_rotating_schedule_and_one_cta_layout_are_bit_identical(sms, pairs, hbv_variant, monkeypatch):
     """hbv_rot_kernel (variant 3: one persistent CTA per SM, the member pairs rotate over its warps, fast warps stop on a
-    shared-memory counter, per-warp TMA rings) and the one-CTA-per-SM launch of hbv_fast2_kernel<2> (variant 5) run the
-    arithmetic of variant 2 member for member: discharge, fused objectives and carried time-slab states must be
-    bit-identical.  RRMPG_B200_HBV_ROT_SMS pretends a GPU of `sms` SMs so that a small ensemble reaches every shape of the
+    shared-memory counter, per-warp TMA rings), the one-CTA-per-SM launches (variant 5: two members per thread, capped and
+    uncapped build; variant 0: what the library picks for the size, one member per thread up to 16 warps per SM) and one
+    member per thread (variant 1) run the arithmetic of variant 2 member for member: discharge, fused objectives and
+    carried time-slab states must be bit-identical.  RRMPG_B200_HBV_ROT_SMS pretends a GPU of `sms` SMs so that a small ensemble reaches every shape of the
     schedule (`pairs` warps per CTA: slow / fast warps, 8- and 16-warp instantiations, a ragged last pair)."""
     monkeypatch.setenv("RRMPG_B200_HBV_ROT_SMS", str(sms))
     N, T = 64 * pairs * sms - 6, 2301
@@ -924,7 +925,7 @@ def test_hbvedu_rotating_schedule_and_one_cta_layout_are_bit_identical(sms, pair
         base = engine.hbvedu(*args, **kw)
         if base.get("qsim") is not None:
             assert_close(base["qsim"], ref, f"variant 2 {sorted(kw)} vs oracle")
-        for v in (3, 5):
+        for v in (0, 1, 3, 5):   # 0 = the library's own choice of members per thread and launch shape for this size
             hbv_variant(v)
             got = engine.hbvedu(*args, **kw)
             for nm in base:
@@ -932,7 +933,7 @@ def test_hbvedu_rotating_schedule_and_one_cta_layout_are_bit_identical(sms, pair
                     assert_bits_equal(got[nm], base[nm], f"variant {v} sms={sms} pairs={pairs} {sorted(kw)} {nm}")
 
 
-@pytest.mark.parametrize("variant", [3, 5])
+@pytest.mark.parametrize("variant", [0, 3, 5])
 def test_hbvedu_layout_variants_leave_flagged_members_to_the_precise_kernel(variant, hbv_variant, monkeypatch):
     """Members outside the FAST contract and soil moistures that leave the table range: hbv_rot_kernel flags the pair (64
     members) and takes it out of its schedule, the one-CTA launch flags its CTA; the PRECISE kernel behind (64-thread
