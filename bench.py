@@ -44,11 +44,12 @@ REF_MEMBERS_PER_WORKER = 384  # numba reference: members per worker process and 
 # fallback for flagged CTAs / non-finite rain, which exits at once on this workload
 LAUNCHES_PER_STEP = {"fast": 3, "precise": 2}
 # Second roofline of the HBV kernel: register-file operand delivery.  Executed warp instructions per
-# member-timestep of hbv_fast2_kernel<2 members/thread, qsim only> on this forcing (ncu, profiles/r02_ncu_full_hbv_v4_*):
-# 49.05 in total, of which 9.84 DFMA (three register operands) and 16.9 other fp64-pipe instructions (DADD / DMUL / DSETP).
-# Measured on the B200 (profiles/r02_fp64_probe_v2.txt): a DFMA with three distinct register operands issues every 3
-# cycles per SM sub-partition, one with a reuse-cached / uniform / immediate operand (and DADD / DMUL) every 2, the rest ~1.
-HBV_INSTR = {"total": 49.05, "dfma": 9.84, "fp64_other": 16.9}
+# member-timestep of hbv_fast2_kernel<1 member/thread, qsim only> (one CTA of 14 warps per SM) on this forcing
+# (ncu source page, profiles/r02_ncu_full_hbv_v5_summary.txt, tools/ncu_instr_mix.py): 52.69 in total, of which 8.87 DFMA with
+# three plain register operands, 0.86 DFMA with a uniform / immediate / reuse-cached operand and 14.03 other fp64-pipe
+# instructions (DADD / DMUL / DSETP / I2F).  Measured on the B200 (profiles/r02_fp64_probe_v2.txt): a DFMA with three distinct
+# register operands issues every 3 cycles per SM sub-partition, the other fp64 instructions every 2, the rest ~1.
+HBV_INSTR = {"total": 52.69, "dfma": 8.87, "fp64_other": 0.86 + 14.03}
 SM_COUNT, SUBPARTITIONS = 148, 4
 
 
@@ -436,7 +437,12 @@ def main():
     bytes_per_launch = BYTES_PER_MEMBER_STEP * (hi - lo) * T_STEPS
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
     traffic = load_profile_json("hbv_traffic.json").get("dram_bytes_per_launch")
-    kernel_name = "rrb::hbv_fast2_kernel<2 members/thread, qsim only>" if args.math == "fast" else "rrb::hbv_precise_kernel<qsim only>"
+    if args.math != "fast":
+        kernel_name = "rrb::hbv_precise_kernel<qsim only>"
+    elif (hi - lo + 31) // 32 <= 16 * SM_COUNT:   # launch_hbvedu: up to 16 member-warps per SM
+        kernel_name = "rrb::hbv_fast2_kernel<1 member/thread, qsim only>, one CTA per SM"
+    else:
+        kernel_name = "rrb::hbv_fast2_kernel<2 members/thread, qsim only>"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name, "kernel_ms": kernel_ms,
                 "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this "
@@ -463,7 +469,8 @@ def main():
                  "load_balance_limit": per_sp / float(int(per_sp) + (per_sp > int(per_sp))),
                  "note": "second roofline, explains the HBM fraction: instruction counts from the committed ncu capture; "
                          "load_balance_limit = mean / max member-warps per SM sub-partition for this ensemble size "
-                         "(65 536 members = 3.46 member-warps per sub-partition, 4 on the busiest)"}
+                         "(65 536 members = 3.46 member-warps per sub-partition, 4 on the busiest: one CTA of 14 warps per SM, "
+                         "warp w on sub-partition w % 4)"}
     cpu = None
     if world == 1 and not args.no_cpu:
         cpu = cpu_baseline_run(f)

@@ -77,7 +77,7 @@ inline int kernel_max_threads(Kernel k) {
 
 // ---- forcing tile geometry (doubles per timestep R, timesteps per tile TT) ----
 constexpr int kAbcR = 1, kAbcTT = 512;
-constexpr int kHbvR = 4, kHbvTT = 128;
+constexpr int kHbvR = 4, kHbvTT = 256;
 constexpr int kGr4jR = 2, kGr4jTT = 256;
 constexpr int kCemaTileDoubles = 1024;  // TT = kCemaTileDoubles / R
 constexpr int kCemaMaxLayers = 16;
