@@ -78,3 +78,24 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), fn
                 assert "liboracle" not in text and "rr_oracle" not in text.replace("oracle/rr_oracle.c header", ""), fn
+
+
+def test_one_cta_per_sm_launch_shape():
+    """rr_kernels.h one_cta_block: the CTA size of a mid-sized single-catchment launch -- ceil(warps / SMs) warps, so that
+    warp w lands on sub-partition w % 4 of its own SM -- and 0 where the shape does not apply (host-side logic, compiled
+    here with the host compiler)."""
+    src = ('#include <stdio.h>\n#include "rr_kernels.h"\nint main(){using rrb::one_cta_block;'
+           'printf("%d %d %d %d %d %d %d %d\\n", one_cta_block(65536, 148, 512, 5), one_cta_block(32768, 148, 512, 5),'
+           'one_cta_block(37888, 148, 512, 9), one_cta_block(104192, 148, 512, 5), one_cta_block(52096, 148, 512, 5),'
+           'one_cta_block(65536, 148, 384, 9), one_cta_block(1786, 4, 512, 5), one_cta_block(65536, 0, 512, 5));return 0;}\n')
+    exe = os.path.join(ROOT, "oracle", "_shape_probe")
+    r = subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "rrmpg_b200", "csrc"), "-I", "/usr/local/cuda/include",
+                        "-x", "c++", "-", "-o", exe], input=src, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    try:
+        got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
+    finally:
+        os.remove(exe)
+    # 2048 warps / 148 SMs -> 14 warps; 1024 -> 7; 8 warps < min 9; 22 warps > 16; 11; 14 warps need 448 > 384 threads;
+    # 56 warps on 4 "SMs" -> 14; sm_count 0 = 148
+    assert got == [448, 224, 0, 0, 352, 0, 448, 448]
