@@ -164,7 +164,7 @@ __global__ void hbv_precise_kernel(const double* __restrict__ F, double snow0, d
     double* s1_o = STORAGE ? out.s1 + off : nullptr;
     double* s2_o = STORAGE ? out.s2 + off : nullptr;
 
-    stream_forcing_regs<kHbvR, kHbvTT, HbvF>(F, t_first, slab.t_end, [&](int64_t t, const HbvF& f) {
+    stream_forcing_regs<kHbvR, kHbvTTSmall, HbvF>(F, t_first, slab.t_end, [&](int64_t t, const HbvF& f) {
         // snow routine, both branches evaluated and selected (hbvedu_model.py:87-96)
         const bool cold = f.temp < T_t;
         const double m = DD * (f.temp - T_t);
@@ -583,7 +583,8 @@ __device__ __forceinline__ HbvPowK hbv_pow_coefficients(uint32_t tb) {
 // [2^-500, 2^500], |Beta| < 32.  Per launch (forcing flag, set by the packer): finite precipitation and temperature.
 // OBJ: 0 = no fused objective, 1 = MSE / NSE (one sum), 2 = KGE (three sums)
 // ------------------------------------------------------------------------------------------------
-template <int MPT, bool WRITEQ, bool STORAGE, int OBJ, int ABL>
+// TT: timesteps per forcing tile (kHbvTT for large CTAs: half the CTA-wide barriers, 1-2 % faster; kHbvTTSmall otherwise)
+template <int MPT, bool WRITEQ, bool STORAGE, int OBJ, int ABL, int TT>
 __device__ __forceinline__ void hbv_fast2_body(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                                                const double* __restrict__ params, int64_t N, HbvOut out, Slab slab, Objective obj,
                                                Batch batch, uint32_t* __restrict__ fflag) {
@@ -645,13 +646,13 @@ __device__ __forceinline__ void hbv_fast2_body(const double* __restrict__ F, dou
     pin(O.row_bytes);
 
     extern __shared__ __align__(128) unsigned char rrb_smem[];
-    uint32_t tb = smem_u32(hbv_tables_to_smem(rrb_smem + forcing_smem_bytes<kHbvR, kHbvTT>()));
+    uint32_t tb = smem_u32(hbv_tables_to_smem(rrb_smem + forcing_smem_bytes<kHbvR, TT>()));
     pin(tb);
     __syncthreads();  // the staged tables are visible
     const HbvPowK pk = hbv_pow_coefficients(tb);
 
     hbv_fast2_loop<MPT, WRITEQ, STORAGE, OBJ, ABL>(P, S, O, tb, pk, obj, [&](auto&& group) __attribute__((always_inline)) {
-        stream_forcing_grouped<kHbvR, kHbvTT, kHbvGroup, HbvF>(F, t_first, slab.t_end, group);
+        stream_forcing_grouped<kHbvR, TT, kHbvGroup, HbvF>(F, t_first, slab.t_end, group);
     });
 
     // did any soil moisture leave the range of the table-driven pow?  Then this CTA's results are void: flag it for
@@ -677,18 +678,18 @@ __device__ __forceinline__ void hbv_fast2_body(const double* __restrict__ F, dou
 // Two compilations of that body.  hbv_fast2_kernel is held to 128 registers (two 256-thread CTAs or one CTA of up to 16
 // warps per SM); hbv_fast2_wide_kernel is not (154 registers for two members per thread): one CTA per SM of at most 12
 // warps, where it is 11 % faster than the capped build (profiles/r02_seasons_ab.txt, 104 192 members).
-template <int MPT, bool WRITEQ, bool STORAGE, int OBJ, int ABL = 0>
+template <int MPT, bool WRITEQ, bool STORAGE, int OBJ, int ABL = 0, int TT = kHbvTTSmall>
 __global__ void __launch_bounds__(512, 1)
 hbv_fast2_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                  const double* __restrict__ params, int64_t N, HbvOut out, Slab slab, Objective obj, Batch batch,
                  uint32_t* __restrict__ fflag) {
-    hbv_fast2_body<MPT, WRITEQ, STORAGE, OBJ, ABL>(F, snow0, soil0, s10, s20, params, N, out, slab, obj, batch, fflag);
+    hbv_fast2_body<MPT, WRITEQ, STORAGE, OBJ, ABL, TT>(F, snow0, soil0, s10, s20, params, N, out, slab, obj, batch, fflag);
 }
 template <bool WRITEQ, int OBJ>
 __global__ void hbv_fast2_wide_kernel(const double* __restrict__ F, double snow0, double soil0, double s10, double s20,
                                       const double* __restrict__ params, int64_t N, HbvOut out, Slab slab, Objective obj,
                                       Batch batch, uint32_t* __restrict__ fflag) {
-    hbv_fast2_body<2, WRITEQ, false, OBJ, 0>(F, snow0, soil0, s10, s20, params, N, out, slab, obj, batch, fflag);
+    hbv_fast2_body<2, WRITEQ, false, OBJ, 0, kHbvTT>(F, snow0, soil0, s10, s20, params, N, out, slab, obj, batch, fflag);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1141,12 +1142,12 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
     int rotw = 0, sm_block = 0;
     bool wide = false;
     if (fast && variant == 3 && slab.t_end < (int64_t(1) << 30)) rotw = rot_warps(N, steps, sms, pair_ok, st, batch, true);
-    if (fast && !rotw && single && cfg.block <= 0 && (variant == 5 || (variant != 1 && variant != 2 && variant != 3))) {
+    if (fast && !rotw && single && (variant == 5 || (variant != 1 && variant != 2 && variant != 3))) {
         const int64_t w1 = warps_per_sm(N), w2 = warps_per_sm(N / 2);
         if (variant != 5 && w1 <= 16) {
             variant = 1;
-            if (w1 >= 5) sm_block = (int)w1 * 32;
-        } else if (pair_ok && w2 <= 16 && (variant == 5 || w2 >= 5)) {
+            if (w1 >= 5 && cfg.block <= 0) sm_block = (int)w1 * 32;  // (a caller's CTA size keeps the member-per-thread choice)
+        } else if (cfg.block <= 0 && pair_ok && w2 <= 16 && (variant == 5 || w2 >= 5)) {
             variant = 2;
             sm_block = (int)w2 * 32;
             wide = !st && w2 <= 12;
@@ -1169,7 +1170,9 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
     // members one flag word stands for
     const int pblock = rotw ? 64 : (sm_block ? 32 : block);
     const dim3 grid_p((unsigned)((N + pblock - 1) / pblock), (unsigned)batch.count);
-    const size_t smem_ring = forcing_smem_bytes<kHbvR, kHbvTT>();
+    const size_t smem_ring = forcing_smem_bytes<kHbvR, kHbvTTSmall>();  // PRECISE and the small-CTA FAST launches
+    const bool big_tiles = block >= 224;  // FAST: 256-step tiles for the large CTAs
+    const size_t smem_ring_fast = big_tiles ? forcing_smem_bytes<kHbvR, kHbvTT>() : smem_ring;
 #define RRB_HBV_ARGS F, inits4[0], inits4[1], inits4[2], inits4[3], params, N, out, slab, obj, batch
 #define RRB_HBV_DISPATCH(LAUNCH_)                          \
     do {                                                   \
@@ -1221,13 +1224,18 @@ cudaError_t launch_hbvedu(const double* F, int64_t T, const double* inits4, cons
 #undef RRB_HBV_ROT
         p_div = 1;
     } else {
-        const size_t smem = smem_ring + hbv_tables_smem_bytes();
+        const size_t smem = (wide ? forcing_smem_bytes<kHbvR, kHbvTT>() : smem_ring_fast) + hbv_tables_smem_bytes();
         const bool kge = ob && obj.kind == RRB_OBJ_KGE_;  // three running sums instead of one
         bool wide_done = false;
 #define RRB_HBV_FAST2(M_, Q_, S_, O_)                                                                                  \
     do {                                                                                                              \
-        if (kge) hbv_fast2_kernel<M_, Q_, S_, (O_) ? 2 : 0><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag);   \
-        else hbv_fast2_kernel<M_, Q_, S_, (O_) ? 1 : 0><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag);       \
+        if (big_tiles) {                                                                                              \
+            if (kge) hbv_fast2_kernel<M_, Q_, S_, (O_) ? 2 : 0, 0, kHbvTT><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag); \
+            else hbv_fast2_kernel<M_, Q_, S_, (O_) ? 1 : 0, 0, kHbvTT><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag);     \
+        } else {                                                                                                      \
+            if (kge) hbv_fast2_kernel<M_, Q_, S_, (O_) ? 2 : 0><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag); \
+            else hbv_fast2_kernel<M_, Q_, S_, (O_) ? 1 : 0><<<grid, block, smem, cfg.stream>>>(RRB_HBV_ARGS, wflag);   \
+        }                                                                                                             \
     } while (0)
 #define RRB_HBV_FAST2A(Q_, S_, O_) RRB_HBV_FAST2(1, Q_, S_, O_)
 #define RRB_HBV_FAST2B(Q_, S_, O_) RRB_HBV_FAST2(2, Q_, S_, O_)

@@ -77,7 +77,9 @@ inline int kernel_max_threads(Kernel k) {
 
 // ---- forcing tile geometry (doubles per timestep R, timesteps per tile TT) ----
 constexpr int kAbcR = 1, kAbcTT = 512;
-constexpr int kHbvR = 4, kHbvTT = 256;
+constexpr int kHbvR = 4, kHbvTT = 256;  // padding unit of the packed forcing = the tile of the large-CTA FAST launches;
+constexpr int kHbvTTSmall = 128;        // small CTAs (and the PRECISE kernel) stream 128-step tiles: 29 instead of 41 KB of
+                                        // shared memory per CTA keeps seven of them resident per SM
 constexpr int kGr4jR = 2, kGr4jTT = 256;
 constexpr int kCemaTileDoubles = 1024;  // TT = kCemaTileDoubles / R
 constexpr int kCemaMaxLayers = 16;
