@@ -1034,7 +1034,7 @@ hbv_rot_kernel(const double* __restrict__ F, double snow0, double soil0, double 
                 if (lane == 0) {
                     if (me_slow) atomicAdd(&ctl->done, 1u);
                     else if (poll && !bad && t_reached < t_end && work_slow == n_slow)
-                        ctl->rho_q8 = (int)(((t_reached - t0) * 256) / share);
+                        atomicExch(&ctl->rho_q8, (int)(((t_reached - t0) * 256) / share));  // any fast warp's ratio will do
                 }
             }
             if (lane == 0) pos_next[p] = reached;
