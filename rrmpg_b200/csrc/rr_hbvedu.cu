@@ -12,11 +12,14 @@
 //                 operation of the reference in the reference's order.
 // MATH = FAST   : same recurrence with the fp64 instruction count cut ~4x: reciprocals of FC / PWP and
 //                 the linear-store coefficients hoisted, explicit FMAs, table-driven pow (rr_math.cuh,
-//                 ~1e-15 relative), and the pow skipped for warps whose members all have
-//                 liquid_water == 0 (then prec_eff = 0 * finite = +0 exactly as in the reference).
+//                 ~1e-15 relative), the pow skipped for warps whose members all have liquid_water == 0
+//                 (then prec_eff = 0 * finite = +0 exactly as in the reference), the snow routine skipped for
+//                 groups of steps that are warm-and-bare or cold for a whole warp (hbv_fast2_loop).
 //                 Discharge stays within rtol 1e-10 of the reference (tests/test_parity_gpu.py).
-// Both: branch-free snow routine, forcing of step t+1 prefetched into registers during step t,
-//       running output pointers, t = 0 peeled out of the time loop.
+// Both: branch-free snow routine, running output addressing, t = 0 peeled out of the time loop.
+// Kernels: hbv_precise_kernel; hbv_fast2_kernel / hbv_fast2_wide_kernel (one or two members per thread, register cap
+// or not) and hbv_rot_kernel (rotating schedule, opt-in) around the shared time loop hbv_fast2_loop; launch_hbvedu
+// picks members per thread and the launch shape from the ensemble size (one CTA per SM for mid-sized ensembles).
 #include "rr_common.cuh"
 #include "rr_kernels.h"
 #include "rr_math.cuh"
