@@ -15,7 +15,10 @@ import sys
 
 KERNELS = [
     # (label, regex on the demangled name)
-    ("HBVEdu FAST, qsim only (bench kernel)", r"hbv_fast_kernel<true, false, false>"),
+    ("HBVEdu FAST, one member per thread, qsim only, 256-step tiles (bench kernel at 65 536 members)",
+     r"hbv_fast2_kernel<1, true, false, 0, 0, 256>"),
+    ("HBVEdu FAST, two members per thread, qsim only, 256-step tiles (1M members)", r"hbv_fast2_kernel<2, true, false, 0, 0, 256>"),
+    ("HBVEdu FAST, rotating schedule, 8 warps, qsim only (opt-in)", r"hbv_rot_kernel<8, true, false, 0>"),
     ("HBVEdu PRECISE, qsim only", r"hbv_precise_kernel<true, false, false>"),
     ("ABC pair kernel (two members per thread)", r"abc_pair_kernel"),
     ("GR4J FAST x4 <= 2.5 class, qsim only", r"gr4j_kernel<rrb::Gr4jMember<3, 7, 0, false>, true, true>"),
