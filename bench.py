@@ -544,6 +544,29 @@ def run_e2e(args, rdist, engine, HBVEdu, f, P_all, n_total, world, rank):
                "api": "rrmpg_b200.models.HBVEdu.simulate(numpy) -> numpy [T, N] (pinned), ONE call for the global ensemble; "
                       + (f"the library shards the members over the {world} GPUs (rrb_opts.n_devices, one worker thread per device), "
                          if world > 1 else "") + "D2H pipelined per time slab"}
+        # the same call as rrmpg_b200.tools.monte_carlo(..., qobs, return_qsim=False) makes it: the per-member objective is
+        # accumulated in the kernel's registers and mse[N] is all that comes back (rrmpg/tools/monte_carlo.py:64-73 loops
+        # simulate + calc_mse over the members).  Host buffers in, host result out, wall clock.
+        qobs = np.abs(np.random.default_rng(11).normal(2.0, 1.0, T_STEPS))
+        def fused_call():
+            with engine.fused(qobs, objective="mse", want_qsim=False) as fz:
+                model.simulate(**kw)
+            return np.asarray(fz.values)
+        try:
+            for _ in range(2):
+                m = fused_call()
+            k_f = 10
+            t0 = time.perf_counter()
+            for _ in range(k_f):
+                m = fused_call()
+            dtf = time.perf_counter() - t0
+            out["fused_objective"] = {"value": n_total * T_STEPS * k_f / dtf, "unit": UNIT, "ms_per_call": dtf / k_f * 1e3,
+                                      "h2d_bytes_per_call": h2d + T_STEPS * 8, "d2h_bytes_per_call": n_total * 8,
+                                      "finite": bool(np.isfinite(m).all()),
+                                      "api": "with engine.fused(qobs, want_qsim=False): HBVEdu.simulate(numpy) -- what "
+                                             "tools.monte_carlo(model, num, qobs, return_qsim=False) runs; result = mse[N] on the host"}
+        except Exception as exc:   # a side figure must never cost the bench line
+            out["fused_objective"] = {"error": repr(exc)}
     rdist.host_barrier()
     return out
 
